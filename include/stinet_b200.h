@@ -1,0 +1,163 @@
+/* stinet_b200.h -- C ABI of the B200-native STINet hot path (libstinet_b200.so).
+ *
+ * The reference (johnpeterflynn/surface-texture-inpainting-net) has NO FFI of its own: its hot path reaches native
+ * code only through torch_geometric / torch_scatter / ATen.  Each entry point below therefore names the reference
+ * call site whose arithmetic it replaces (paths relative to the reference repo root).  The Python modules in
+ * stinet_b200/models mirror the reference's module API and call these functions through ctypes (stinet_b200/_abi.py).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch allocates inputs, outputs and workspaces);
+ *    the library never allocates, frees or synchronises, and launches only on the given stream;
+ *  - matrices are row-major fp32 with an explicit leading dimension `ld*` counted in ELEMENTS (so column slices of a
+ *    wider buffer can be passed); index arrays produced by the library are int32; index arrays coming from the
+ *    reference's data pipeline are int64 (edge_index, trace maps) and are narrowed once by stinet_csr_build;
+ *  - return value: 0 = ok, <0 = error (STINET_ERR_*); stinet_last_error() gives a thread-local message;
+ *    no exception crosses the ABI.  Functions are re-entrant and stream-ordered; the library has no mutable global
+ *    state apart from per-kernel function attributes set once.
+ *  - `status` (nullable, int32[1] on the device): kernels OR a bit into it on data-dependent errors
+ *    (bit0: index out of range) because reporting them through the return value would need a sync.
+ */
+#ifndef STINET_B200_H
+#define STINET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STINET_ABI_VERSION 1
+
+#define STINET_OK 0
+#define STINET_ERR_ARG (-1)          /* null pointer, negative size, bad enum */
+#define STINET_ERR_UNSUPPORTED (-2)  /* shape / alignment the kernels do not cover */
+#define STINET_ERR_CUDA (-3)         /* launch failed; message holds cudaGetErrorString */
+#define STINET_ERR_WORKSPACE (-4)    /* workspace too small */
+
+typedef void* stinet_stream_t; /* cudaStream_t */
+
+enum { STINET_REDUCE_ADD = 0, STINET_REDUCE_MEAN = 1, STINET_REDUCE_MAX = 2 };
+enum { STINET_PREC_FP32 = 0, STINET_PREC_BF16 = 1 };  /* arithmetic of the dense layers; accumulation is always fp32 */
+enum { STINET_ACT_NONE = 0, STINET_ACT_ELU = 1 };
+
+int stinet_abi_version(void);
+const char* stinet_last_error(void);
+/* 1 iff the running device is compute capability 10.x (the only target this library is built for). */
+int stinet_device_ok(void);
+/* process-wide number of kernels this library has launched so far (bench.py's `gpu_launches`) */
+long long stinet_launch_count(void);
+
+/* ---- structure: CSR builder (no reference counterpart; replaces the COO edge_index that PyG's
+ * MessagePassing.propagate consumes, call sites models/modules/edge_conv_filter.py:57, sage_conv_filter.py:75 and
+ * the trace maps consumed by torch_scatter at models/surfacetextureinpaintingnet.py:384,386,422).
+ * Groups the positions 0..n_items-1 by key[pos] in [0,n_rows), STABLY (original order kept inside a row, which
+ * reproduces torch_scatter's CPU summation / tie-break order):
+ *   rowptr[n_rows+1], perm[n_items] (positions grouped by key), col[n_items] = (int32) other[perm[k]] (if other != NULL),
+ *   key32[n_items] = (int32) key[pos] (if key32 != NULL). */
+size_t stinet_csr_workspace_bytes(int64_t n_rows, int64_t n_items);
+int stinet_csr_build(const int64_t* key, const int64_t* other, int64_t n_items, int64_t n_rows, int32_t* rowptr,
+                     int32_t* perm, int32_t* col, int32_t* key32, int32_t* status, void* workspace,
+                     size_t workspace_bytes, stinet_stream_t stream);
+/* ---- aggregation over CSR rows (replaces PyG propagate's scatter(msg, edge_index[1], reduce=...) =
+ * torch_scatter.scatter_{sum,mean,max}; call sites edge_conv_filter.py:57 (mean), sage_conv_filter.py:75 (mean),
+ * utils/metrics/graph_metrics.py:12 (add)).  out[i,:] = reduce_{k in row i} x[col[k],:]; mean = sum/max(deg,1);
+ * rows without entries give 0.  max: arg[i,c] = ORIGINAL edge id (eid[k]) of the first edge attaining the maximum,
+ * n_items for empty rows (torch_scatter CPU semantics). */
+int stinet_aggregate_fwd(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* eid,
+                         int64_t n_rows, int64_t n_items, int64_t channels, int reduce, float* out, int64_t ldo,
+                         int32_t* arg, stinet_stream_t stream);
+/* dx[j,:] = sum over out-edges (j->i) of g[i,:] * w, w = 1 (add), 1/max(deg_t(i),1) (mean), [arg[i,c]==eid] (max).
+ * rowptr_s/col_s/eid_s: CSR grouped by SOURCE (col_s = target of each out-edge); rowptr_t: CSR by target (degrees). */
+int stinet_aggregate_bwd(const float* g, int64_t ldg, const int32_t* rowptr_s, const int32_t* col_s,
+                         const int32_t* eid_s, const int32_t* rowptr_t, const int32_t* arg, int64_t n_src_rows,
+                         int64_t channels, int reduce, float* dx, int64_t lddx, stinet_stream_t stream);
+
+/* ---- fused EdgeConv message stage (replaces x_j/x_i gathers + cat + Linear + ReLU + scatter-mean of PyG
+ * EdgeConv.message/aggregate, models/modules/edge_conv_filter.py:46-57, edge_conv_translation_invariance.py:19-21,
+ * in the hoisted form  nn.0([x_i || x_j-x_i]) = P_i + Q_j,  P = X(Wa-Wb)^T + b, Q = X Wb^T):
+ *   hid[i,:] = (1/max(deg_i,1)) * sum_{j->i} relu(P[i,:] + Q[j,:]) */
+int stinet_edge_message_fwd(const float* P, int64_t ldp, const float* Q, int64_t ldq, const int32_t* rowptr_t,
+                            const int32_t* col_t, int64_t n_rows, int64_t hidden, float* hid, int64_t ldh,
+                            stinet_stream_t stream);
+/* dP[i,:] = (1/deg_i) * sum_{j->i} dhid[i,:] * [P_i+Q_j > 0]                    (CSR by target) */
+int stinet_edge_message_bwd_target(const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* dhid,
+                                   int64_t ldd, const int32_t* rowptr_t, const int32_t* col_t, int64_t n_rows,
+                                   int64_t hidden, float* dP, int64_t lddp, stinet_stream_t stream);
+/* dQ[j,:] = sum_{j->i} (1/deg_i) * dhid[i,:] * [P_i+Q_j > 0]                    (CSR by source) */
+int stinet_edge_message_bwd_source(const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* dhid,
+                                   int64_t ldd, const int32_t* rowptr_t, const int32_t* rowptr_s,
+                                   const int32_t* col_s, int64_t n_rows, int64_t hidden, float* dQ, int64_t lddq,
+                                   stinet_stream_t stream);
+
+/* ---- trace-map pooling / unpooling (replaces SurfaceTextureInpaintingNet._pooling / _unpooling,
+ * models/surfacetextureinpaintingnet.py:382-391 = torch_scatter.scatter_max / scatter_mean / x[trace]).
+ * Cluster CSR: rowptr_c[n_coarse+1], member[n_fine] = fine vertex ids grouped by cluster in ascending order
+ * (stinet_csr_build with key = trace).  pool-max: arg[c,ch] = LOWEST fine id attaining the max, n_fine if empty. */
+int stinet_pool_max_fwd(const float* x, int64_t ldx, const int32_t* rowptr_c, const int32_t* member, int64_t n_fine,
+                        int64_t n_coarse, int64_t channels, float* out, int64_t ldo, int32_t* arg,
+                        stinet_stream_t stream);
+int stinet_pool_max_bwd(const float* g, int64_t ldg, const int32_t* arg, const int32_t* trace32, int64_t n_fine,
+                        int64_t channels, float* dx, int64_t lddx, stinet_stream_t stream);
+int stinet_pool_mean_fwd(const float* x, int64_t ldx, const int32_t* rowptr_c, const int32_t* member,
+                         int64_t n_coarse, int64_t channels, float* out, int64_t ldo, stinet_stream_t stream);
+int stinet_pool_mean_bwd(const float* g, int64_t ldg, const int32_t* rowptr_c, const int32_t* trace32,
+                         int64_t n_fine, int64_t channels, float* dx, int64_t lddx, stinet_stream_t stream);
+/* integer variant used for the per-vertex graph id (`batch = scatter_max(batch, trace)`, :422); empty cluster -> 0 */
+int stinet_pool_max_i32(const int32_t* v, const int32_t* rowptr_c, const int32_t* member, int64_t n_coarse,
+                        int32_t* out, stinet_stream_t stream);
+/* out[i, col_off:col_off+channels] = xc[trace32[i], :]  (unpool; a col_off/ldo pair gives the skip-concat variant of
+ * models/singleconvmeshnet.py:140-141) */
+int stinet_unpool_fwd(const float* xc, int64_t ldc, const int32_t* trace32, int64_t n_fine, int64_t channels,
+                      float* out, int64_t ldo, stinet_stream_t stream);
+/* dxc[c,:] = sum_{i in cluster c} g[i,:]   (ascending member order; replaces index_add_ atomics) */
+int stinet_unpool_bwd(const float* g, int64_t ldg, const int32_t* rowptr_c, const int32_t* member, int64_t n_coarse,
+                      int64_t channels, float* dxc, int64_t ldd, stinet_stream_t stream);
+
+/* ---- per-graph instance norm (replaces FastInstanceNorm.forward, models/modules/fastinstancenorm.py:42-107)
+ * Rows are partitioned twice, exactly as the reference does: `slice_ptr` (= torch.linspace(0,N,B+1), :53) bounds the
+ * ranges the sums run over, `gid[r]` (= batch[r]; NULL = all zero) selects which mean / rstd a row uses (:73,:99),
+ * and `cnt[s]` (= degree(batch).clamp(min=1), :60) is the divisor.  biased variance, eps inside the sqrt.
+ *   mean[s,c] = sum_{r in slice s} x[r,c] / cnt[s];  var[s,c] = sum_{r in slice s} (x[r,c]-mean[gid[r],c])^2 / cnt[s]
+ *   rstd = 1/sqrt(var+eps). */
+size_t stinet_segnorm_workspace_bytes(int64_t max_seg_rows, int64_t channels, int64_t n_seg);
+/* max_seg_rows: host-known upper bound of the slice lengths (sizes the grid without a device read).
+ * gid == NULL: a row uses the statistics of the slice that contains it. */
+int stinet_segnorm_stats(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
+                         int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, const int32_t* gid,
+                         float eps, float* mean, float* rstd, void* workspace, size_t workspace_bytes,
+                         stinet_stream_t stream);
+/* out = residual + act((x - mean[g]) * rstd[g])   (residual nullable; act = STINET_ACT_*): the tail of
+ * GraphResnetBlock.forward, models/surfacetextureinpaintingnet.py:510-521.  g = gid[r] (NULL: segment 0);
+ * mean == rstd == NULL: identity norm (norm_type 'none', :257-263). */
+int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, const int32_t* gid,
+                         const float* mean, const float* rstd, const float* residual, int64_t ldr, int act,
+                         float* out, int64_t ldo, stinet_stream_t stream);
+/* backward of out = act(norm(x)):  dx = rstd*(dz - mean_s(dz) - yhat*mean_s(dz*yhat)), dz = dout*act'(yhat).
+ * Requires slices == true segments (gid constant on every slice); otherwise STINET_ERR_UNSUPPORTED is the
+ * caller's job to raise (the library cannot see it without a sync). */
+int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows, int64_t channels,
+                       int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt,
+                       const int32_t* gid, const float* mean, const float* rstd, int act, float* dx, int64_t lddx,
+                       void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+
+/* ---- dense layers (replace torch.nn.Linear inside the message MLP, the shortcut and the head:
+ * models/modules/edge_conv_filter.py:46-55, models/surfacetextureinpaintingnet.py:504-505,356-358).
+ * fwd:   C[M,N]  = A[M,K] W[N,K]^T + bias[N] * (rowmask ? rowmask[m] > 0 : 1)
+ * dgrad: dA[M,K] = dC[M,N] W[N,K]
+ * wgrad: dW[N,K] = dC[M,N]^T A[M,K];  dbias[N] = sum_m dC[m,:] * (rowmask ? rowmask[m] > 0 : 1)   (dbias nullable) */
+size_t stinet_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision);
+int stinet_linear_fwd(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                      const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int precision,
+                      void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+int stinet_linear_dgrad(const float* dC, int64_t ldc, const float* W, int64_t ldw, float* dA, int64_t lda, int64_t M,
+                        int64_t N, int64_t K, int precision, void* workspace, size_t workspace_bytes,
+                        stinet_stream_t stream);
+int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t lda, const int32_t* rowmask, float* dW,
+                        int64_t ldw, float* dbias, int64_t M, int64_t N, int64_t K, int precision, void* workspace,
+                        size_t workspace_bytes, stinet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STINET_B200_H */

@@ -1,0 +1,370 @@
+// Segmented aggregation over CSR rows and the fused EdgeConv message stage.
+// One warp owns one CSR row and strides over the channel dimension in float4 (or scalar) columns; a row's entries
+// are accumulated sequentially in CSR order (= original edge order), so results are deterministic and follow the
+// summation order of torch_scatter's CPU kernels.  No atomics anywhere.
+#include "common.cuh"
+
+namespace stinet {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kAggThreads = kWarpsPerCta * 32;
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+// true division (not reciprocal-multiply): the reference divides sums by counts, keep the same rounding
+__device__ __forceinline__ float4 f4_div(float4 a, float d) { return make_float4(a.x / d, a.y / d, a.z / d, a.w / d); }
+__device__ __forceinline__ float relu(float v) { return v > 0.f ? v : 0.f; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// generic aggregate: out[i,:] = reduce_k x[col[k],:]
+
+template <int REDUCE, bool VEC>
+__global__ void __launch_bounds__(kAggThreads)
+aggregate_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowptr,
+                     const int32_t* __restrict__ col, const int32_t* __restrict__ eid, int64_t n_rows,
+                     int32_t n_items, int channels, float* __restrict__ out, int64_t ldo, int32_t* __restrict__ arg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const float den = (REDUCE == STINET_REDUCE_MEAN) ? (float)max(end - beg, 1) : 1.f;
+    if (VEC) {
+      const int c4n = channels >> 2;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = beg;
+        for (; k + 4 <= end; k += 4) {
+          int j0 = col[k], j1 = col[k + 1], j2 = col[k + 2], j3 = col[k + 3];
+          float4 v0 = reinterpret_cast<const float4*>(x + j0 * ldx)[c4];
+          float4 v1 = reinterpret_cast<const float4*>(x + j1 * ldx)[c4];
+          float4 v2 = reinterpret_cast<const float4*>(x + j2 * ldx)[c4];
+          float4 v3 = reinterpret_cast<const float4*>(x + j3 * ldx)[c4];
+          acc = f4_add(f4_add(f4_add(f4_add(acc, v0), v1), v2), v3);
+        }
+        for (; k < end; ++k) acc = f4_add(acc, reinterpret_cast<const float4*>(x + (int64_t)col[k] * ldx)[c4]);
+        reinterpret_cast<float4*>(out + i * ldo)[c4] = f4_div(acc, den);
+      }
+    } else {
+      for (int c = lane; c < channels; c += 32) {
+        if (REDUCE == STINET_REDUCE_MAX) {
+          float best = -3.402823466e+38f;
+          int32_t best_e = n_items;
+          for (int k = beg; k < end; ++k) {
+            float v = x[(int64_t)col[k] * ldx + c];
+            if (v > best) {
+              best = v;
+              best_e = eid[k];
+            }
+          }
+          out[i * ldo + c] = (best_e == n_items) ? 0.f : best;
+          arg[i * (int64_t)channels + c] = best_e;
+        } else {
+          float acc = 0.f;
+          for (int k = beg; k < end; ++k) acc += x[(int64_t)col[k] * ldx + c];
+          out[i * ldo + c] = acc / den;
+        }
+      }
+    }
+  }
+}
+
+// dx[j,:] = sum_{out-edges j->i} w * g[i,:]
+template <int REDUCE, bool VEC>
+__global__ void __launch_bounds__(kAggThreads)
+aggregate_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __restrict__ rowptr_s,
+                     const int32_t* __restrict__ col_s, const int32_t* __restrict__ eid_s,
+                     const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ arg, int64_t n_rows,
+                     int channels, float* __restrict__ dx, int64_t lddx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t j = warp0; j < n_rows; j += nwarps) {
+    const int beg = rowptr_s[j], end = rowptr_s[j + 1];
+    if (VEC) {
+      const int c4n = channels >> 2;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = beg; k < end; ++k) {
+          const int i = col_s[k];
+          float den = 1.f;
+          if (REDUCE == STINET_REDUCE_MEAN) den = (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
+          float4 v = reinterpret_cast<const float4*>(g + (int64_t)i * ldg)[c4];
+          acc = f4_add(acc, f4_div(v, den));
+        }
+        reinterpret_cast<float4*>(dx + j * lddx)[c4] = acc;
+      }
+    } else {
+      for (int c = lane; c < channels; c += 32) {
+        float acc = 0.f;
+        for (int k = beg; k < end; ++k) {
+          const int i = col_s[k];
+          float v = g[(int64_t)i * ldg + c];
+          if (REDUCE == STINET_REDUCE_MEAN) v /= (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
+          if (REDUCE == STINET_REDUCE_MAX) v = (arg[(int64_t)i * channels + c] == eid_s[k]) ? v : 0.f;
+          acc += v;
+        }
+        dx[j * lddx + c] = acc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused EdgeConv message stage
+
+template <bool VEC>
+__global__ void __launch_bounds__(kAggThreads)
+edge_message_fwd_kernel(const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+                        const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+                        int hidden, float* __restrict__ hid, int64_t ldh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const float den = (float)max(end - beg, 1);
+    if (VEC) {
+      const int c4n = hidden >> 2;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        const float4 p = reinterpret_cast<const float4*>(P + i * ldp)[c4];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = beg;
+        for (; k + 4 <= end; k += 4) {
+          int j0 = col[k], j1 = col[k + 1], j2 = col[k + 2], j3 = col[k + 3];
+          float4 q0 = reinterpret_cast<const float4*>(Q + j0 * ldq)[c4];
+          float4 q1 = reinterpret_cast<const float4*>(Q + j1 * ldq)[c4];
+          float4 q2 = reinterpret_cast<const float4*>(Q + j2 * ldq)[c4];
+          float4 q3 = reinterpret_cast<const float4*>(Q + j3 * ldq)[c4];
+          acc.x += relu(p.x + q0.x); acc.y += relu(p.y + q0.y); acc.z += relu(p.z + q0.z); acc.w += relu(p.w + q0.w);
+          acc.x += relu(p.x + q1.x); acc.y += relu(p.y + q1.y); acc.z += relu(p.z + q1.z); acc.w += relu(p.w + q1.w);
+          acc.x += relu(p.x + q2.x); acc.y += relu(p.y + q2.y); acc.z += relu(p.z + q2.z); acc.w += relu(p.w + q2.w);
+          acc.x += relu(p.x + q3.x); acc.y += relu(p.y + q3.y); acc.z += relu(p.z + q3.z); acc.w += relu(p.w + q3.w);
+        }
+        for (; k < end; ++k) {
+          float4 q = reinterpret_cast<const float4*>(Q + (int64_t)col[k] * ldq)[c4];
+          acc.x += relu(p.x + q.x); acc.y += relu(p.y + q.y); acc.z += relu(p.z + q.z); acc.w += relu(p.w + q.w);
+        }
+        reinterpret_cast<float4*>(hid + i * ldh)[c4] = f4_div(acc, den);
+      }
+    } else {
+      for (int c = lane; c < hidden; c += 32) {
+        const float p = P[i * ldp + c];
+        float acc = 0.f;
+        for (int k = beg; k < end; ++k) acc += relu(p + Q[(int64_t)col[k] * ldq + c]);
+        hid[i * ldh + c] = acc / den;
+      }
+    }
+  }
+}
+
+// dP[i,:] = (1/deg_i) * dhid[i,:] * #{j->i : P_i+Q_j > 0}   (per channel)
+template <bool VEC>
+__global__ void __launch_bounds__(kAggThreads)
+edge_message_bwd_target_kernel(const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+                               const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr,
+                               const int32_t* __restrict__ col, int64_t n_rows, int hidden, float* __restrict__ dP,
+                               int64_t lddp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const float den = (float)max(end - beg, 1);
+    if (VEC) {
+      const int c4n = hidden >> 2;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        const float4 p = reinterpret_cast<const float4*>(P + i * ldp)[c4];
+        const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + i * ldd)[c4], den);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = beg; k < end; ++k) {
+          float4 q = reinterpret_cast<const float4*>(Q + (int64_t)col[k] * ldq)[c4];
+          acc.x += (p.x + q.x > 0.f) ? d.x : 0.f;
+          acc.y += (p.y + q.y > 0.f) ? d.y : 0.f;
+          acc.z += (p.z + q.z > 0.f) ? d.z : 0.f;
+          acc.w += (p.w + q.w > 0.f) ? d.w : 0.f;
+        }
+        reinterpret_cast<float4*>(dP + i * lddp)[c4] = acc;
+      }
+    } else {
+      for (int c = lane; c < hidden; c += 32) {
+        const float p = P[i * ldp + c];
+        const float d = dhid[i * ldd + c] / den;
+        float acc = 0.f;
+        for (int k = beg; k < end; ++k) acc += (p + Q[(int64_t)col[k] * ldq + c] > 0.f) ? d : 0.f;
+        dP[i * lddp + c] = acc;
+      }
+    }
+  }
+}
+
+// dQ[j,:] = sum_{j->i} (1/deg_i) * dhid[i,:] * [P_i+Q_j > 0]
+template <bool VEC>
+__global__ void __launch_bounds__(kAggThreads)
+edge_message_bwd_source_kernel(const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+                               const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr_t,
+                               const int32_t* __restrict__ rowptr_s, const int32_t* __restrict__ col_s,
+                               int64_t n_rows, int hidden, float* __restrict__ dQ, int64_t lddq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t j = warp0; j < n_rows; j += nwarps) {
+    const int beg = rowptr_s[j], end = rowptr_s[j + 1];
+    if (VEC) {
+      const int c4n = hidden >> 2;
+      for (int c4 = lane; c4 < c4n; c4 += 32) {
+        const float4 q = reinterpret_cast<const float4*>(Q + j * ldq)[c4];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = beg; k < end; ++k) {
+          const int i = col_s[k];
+          const float den = (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
+          const float4 p = reinterpret_cast<const float4*>(P + (int64_t)i * ldp)[c4];
+          const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + (int64_t)i * ldd)[c4], den);
+          acc.x += (p.x + q.x > 0.f) ? d.x : 0.f;
+          acc.y += (p.y + q.y > 0.f) ? d.y : 0.f;
+          acc.z += (p.z + q.z > 0.f) ? d.z : 0.f;
+          acc.w += (p.w + q.w > 0.f) ? d.w : 0.f;
+        }
+        reinterpret_cast<float4*>(dQ + j * lddq)[c4] = acc;
+      }
+    } else {
+      for (int c = lane; c < hidden; c += 32) {
+        const float q = Q[j * ldq + c];
+        float acc = 0.f;
+        for (int k = beg; k < end; ++k) {
+          const int i = col_s[k];
+          const float den = (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
+          acc += (P[(int64_t)i * ldp + c] + q > 0.f) ? dhid[(int64_t)i * ldd + c] / den : 0.f;
+        }
+        dQ[j * lddq + c] = acc;
+      }
+    }
+  }
+}
+
+inline bool vec_ok(int64_t channels, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
+  if (channels & 3) return false;
+  for (auto p : ptrs)
+    if (!aligned16(p)) return false;
+  for (auto l : lds)
+    if (l & 3) return false;
+  return true;
+}
+
+inline int row_grid(int64_t n_rows) { return wave_grid(n_rows, kWarpsPerCta, 8, 16); }
+
+}  // namespace stinet
+
+using namespace stinet;
+
+extern "C" int stinet_aggregate_fwd(const float* x, int64_t ldx, const int32_t* rowptr, const int32_t* col,
+                                    const int32_t* eid, int64_t n_rows, int64_t n_items, int64_t channels,
+                                    int reduce, float* out, int64_t ldo, int32_t* arg, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && rowptr && out && (col || n_items == 0), STINET_ERR_ARG, "aggregate_fwd: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldx >= channels && ldo >= channels, STINET_ERR_ARG,
+                 "aggregate_fwd: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const int g = row_grid(n_rows);
+  const int ch = (int)channels;
+  const bool v = vec_ok(channels, {x, out}, {ldx, ldo});
+  switch (reduce) {
+    case STINET_REDUCE_ADD:
+      if (v) K(aggregate_fwd_kernel<STINET_REDUCE_ADD, true><<<g, kAggThreads, 0, s>>>(x, ldx, rowptr, col, eid, n_rows, (int32_t)n_items, ch, out, ldo, arg));
+      else K(aggregate_fwd_kernel<STINET_REDUCE_ADD, false><<<g, kAggThreads, 0, s>>>(x, ldx, rowptr, col, eid, n_rows, (int32_t)n_items, ch, out, ldo, arg));
+      break;
+    case STINET_REDUCE_MEAN:
+      if (v) K(aggregate_fwd_kernel<STINET_REDUCE_MEAN, true><<<g, kAggThreads, 0, s>>>(x, ldx, rowptr, col, eid, n_rows, (int32_t)n_items, ch, out, ldo, arg));
+      else K(aggregate_fwd_kernel<STINET_REDUCE_MEAN, false><<<g, kAggThreads, 0, s>>>(x, ldx, rowptr, col, eid, n_rows, (int32_t)n_items, ch, out, ldo, arg));
+      break;
+    case STINET_REDUCE_MAX:
+      STINET_REQUIRE(arg && eid, STINET_ERR_ARG, "aggregate_fwd(max): arg and eid are required");
+      K(aggregate_fwd_kernel<STINET_REDUCE_MAX, false><<<g, kAggThreads, 0, s>>>(x, ldx, rowptr, col, eid, n_rows, (int32_t)n_items, ch, out, ldo, arg));
+      break;
+    default:
+      STINET_REQUIRE(false, STINET_ERR_ARG, "aggregate_fwd: unknown reduce %d", reduce);
+  }
+  return check_launch("aggregate_fwd");
+}
+
+extern "C" int stinet_aggregate_bwd(const float* g_, int64_t ldg, const int32_t* rowptr_s, const int32_t* col_s,
+                                    const int32_t* eid_s, const int32_t* rowptr_t, const int32_t* arg,
+                                    int64_t n_rows, int64_t channels, int reduce, float* dx, int64_t lddx,
+                                    stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(g_ && rowptr_s && dx, STINET_ERR_ARG, "aggregate_bwd: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldg >= channels && lddx >= channels, STINET_ERR_ARG,
+                 "aggregate_bwd: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const int g = row_grid(n_rows);
+  const int ch = (int)channels;
+  const bool v = vec_ok(channels, {g_, dx}, {ldg, lddx});
+  switch (reduce) {
+    case STINET_REDUCE_ADD:
+      if (v) K(aggregate_bwd_kernel<STINET_REDUCE_ADD, true><<<g, kAggThreads, 0, s>>>(g_, ldg, rowptr_s, col_s, eid_s, rowptr_t, arg, n_rows, ch, dx, lddx));
+      else K(aggregate_bwd_kernel<STINET_REDUCE_ADD, false><<<g, kAggThreads, 0, s>>>(g_, ldg, rowptr_s, col_s, eid_s, rowptr_t, arg, n_rows, ch, dx, lddx));
+      break;
+    case STINET_REDUCE_MEAN:
+      STINET_REQUIRE(rowptr_t, STINET_ERR_ARG, "aggregate_bwd(mean): rowptr_t required");
+      if (v) K(aggregate_bwd_kernel<STINET_REDUCE_MEAN, true><<<g, kAggThreads, 0, s>>>(g_, ldg, rowptr_s, col_s, eid_s, rowptr_t, arg, n_rows, ch, dx, lddx));
+      else K(aggregate_bwd_kernel<STINET_REDUCE_MEAN, false><<<g, kAggThreads, 0, s>>>(g_, ldg, rowptr_s, col_s, eid_s, rowptr_t, arg, n_rows, ch, dx, lddx));
+      break;
+    case STINET_REDUCE_MAX:
+      STINET_REQUIRE(arg && eid_s, STINET_ERR_ARG, "aggregate_bwd(max): arg and eid_s required");
+      K(aggregate_bwd_kernel<STINET_REDUCE_MAX, false><<<g, kAggThreads, 0, s>>>(g_, ldg, rowptr_s, col_s, eid_s, rowptr_t, arg, n_rows, ch, dx, lddx));
+      break;
+    default:
+      STINET_REQUIRE(false, STINET_ERR_ARG, "aggregate_bwd: unknown reduce %d", reduce);
+  }
+  return check_launch("aggregate_bwd");
+}
+
+extern "C" int stinet_edge_message_fwd(const float* P, int64_t ldp, const float* Q, int64_t ldq,
+                                       const int32_t* rowptr_t, const int32_t* col_t, int64_t n_rows,
+                                       int64_t hidden, float* hid, int64_t ldh, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(P && Q && rowptr_t && hid, STINET_ERR_ARG, "edge_message_fwd: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden && ldh >= hidden, STINET_ERR_ARG,
+                 "edge_message_fwd: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const int g = row_grid(n_rows);
+  if (vec_ok(hidden, {P, Q, hid}, {ldp, ldq, ldh}))
+    K(edge_message_fwd_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, rowptr_t, col_t, n_rows, (int)hidden, hid, ldh));
+  else
+    K(edge_message_fwd_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, rowptr_t, col_t, n_rows, (int)hidden, hid, ldh));
+  return check_launch("edge_message_fwd");
+}
+
+extern "C" int stinet_edge_message_bwd_target(const float* P, int64_t ldp, const float* Q, int64_t ldq,
+                                              const float* dhid, int64_t ldd, const int32_t* rowptr_t,
+                                              const int32_t* col_t, int64_t n_rows, int64_t hidden, float* dP,
+                                              int64_t lddp, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(P && Q && dhid && rowptr_t && dP, STINET_ERR_ARG, "edge_message_bwd_target: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden && ldd >= hidden && lddp >= hidden,
+                 STINET_ERR_ARG, "edge_message_bwd_target: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const int g = row_grid(n_rows);
+  if (vec_ok(hidden, {P, Q, dhid, dP}, {ldp, ldq, ldd, lddp}))
+    K(edge_message_bwd_target_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, col_t, n_rows, (int)hidden, dP, lddp));
+  else
+    K(edge_message_bwd_target_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, col_t, n_rows, (int)hidden, dP, lddp));
+  return check_launch("edge_message_bwd_target");
+}
+
+extern "C" int stinet_edge_message_bwd_source(const float* P, int64_t ldp, const float* Q, int64_t ldq,
+                                              const float* dhid, int64_t ldd, const int32_t* rowptr_t,
+                                              const int32_t* rowptr_s, const int32_t* col_s, int64_t n_rows,
+                                              int64_t hidden, float* dQ, int64_t lddq, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(P && Q && dhid && rowptr_t && rowptr_s && dQ, STINET_ERR_ARG, "edge_message_bwd_source: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden && ldd >= hidden && lddq >= hidden,
+                 STINET_ERR_ARG, "edge_message_bwd_source: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const int g = row_grid(n_rows);
+  if (vec_ok(hidden, {P, Q, dhid, dQ}, {ldp, ldq, ldd, lddq}))
+    K(edge_message_bwd_source_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, rowptr_s, col_s, n_rows, (int)hidden, dQ, lddq));
+  else
+    K(edge_message_bwd_source_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, rowptr_s, col_s, n_rows, (int)hidden, dQ, lddq));
+  return check_launch("edge_message_bwd_source");
+}

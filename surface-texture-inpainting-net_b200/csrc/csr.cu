@@ -1,0 +1,246 @@
+// CSR builder: stable grouping of positions by an int64 key (edge target / edge source / trace id).
+//   count (atomic histogram, order-independent) -> exclusive scan -> atomic fill -> per-row sort by position.
+// The final per-row sort makes the result independent of atomic arrival order: rows list their members in
+// ascending original position, i.e. exactly `argsort(key, stable=True)` (oracle: csr_by_key).
+#include "common.cuh"
+
+namespace stinet {
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+constexpr int kSmallRow = 64;  // rows up to this length are sorted by one thread
+
+__global__ void csr_count_kernel(const int64_t* __restrict__ key, int64_t n_items, int64_t n_rows,
+                                 int32_t* __restrict__ cnt, int32_t* __restrict__ key32,
+                                 int32_t* __restrict__ status) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_items;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = key[e];
+    bool ok = (t >= 0) & (t < n_rows);
+    if (key32) key32[e] = ok ? (int32_t)t : 0;
+    if (ok) {
+      atomicAdd(&cnt[t], 1);
+    } else if (status) {
+      atomicOr(status, 1);
+    }
+  }
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// inclusive scan of one value per thread across the block; returns the inclusive prefix, *total = block sum
+__device__ __forceinline__ int block_incl_scan(int v, int* total) {
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = warp_incl_scan(v);
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+    w = warp_incl_scan(w);
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  int off = wid ? wsum[wid - 1] : 0;
+  *total = wsum[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return inc + off;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_chunk_sums(const int32_t* __restrict__ cnt, int64_t n,
+                                                                 int32_t* __restrict__ chunk_sum) {
+  int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < n) s += cnt[base + k];
+  int total;
+  block_incl_scan(s, &total);
+  if (threadIdx.x == 0) chunk_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_chunk_offsets(int32_t* __restrict__ chunk_sum, int n_chunks) {
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n_chunks; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    int v = i < n_chunks ? chunk_sum[i] : 0;
+    int total;
+    int inc = block_incl_scan(v, &total);
+    int carry = carry_s;
+    if (i < n_chunks) chunk_sum[i] = carry + inc - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + total;
+    __syncthreads();
+  }
+}
+
+// rowptr[i] = sum_{k<i} cnt[k] for i in [0, n_rows]  (n = n_rows + 1 outputs; cnt[n_rows] is read as 0)
+__global__ void __launch_bounds__(kScanThreads) scan_write(const int32_t* __restrict__ cnt, int64_t n_rows,
+                                                           const int32_t* __restrict__ chunk_off,
+                                                           int32_t* __restrict__ rowptr) {
+  int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n_rows) ? cnt[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int inc = block_incl_scan(s, &total);
+  int run = chunk_off[blockIdx.x] + inc - s;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k <= n_rows) rowptr[base + k] = run;
+    run += v[k];
+  }
+}
+
+__global__ void csr_fill_kernel(const int64_t* __restrict__ key, int64_t n_items, int64_t n_rows,
+                                const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
+                                int32_t* __restrict__ perm) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_items;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = key[e];
+    if (t < 0 || t >= n_rows) continue;
+    int pos = atomicAdd(&cursor[t], 1);
+    perm[rowptr[t] + pos] = (int32_t)e;
+  }
+}
+
+// one thread per row: insertion sort of short rows; long rows are queued for the block-level rank sort
+__global__ void csr_sort_small_rows(const int32_t* __restrict__ rowptr, int64_t n_rows, int32_t* __restrict__ perm,
+                                    int32_t* __restrict__ big_rows, int32_t* __restrict__ n_big) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int beg = rowptr[r], end = rowptr[r + 1];
+    int d = end - beg;
+    if (d <= 1) continue;
+    if (d > kSmallRow) {
+      big_rows[atomicAdd(n_big, 1)] = (int32_t)r;
+      continue;
+    }
+    for (int a = beg + 1; a < end; ++a) {
+      int v = perm[a];
+      int b = a - 1;
+      while (b >= beg && perm[b] > v) {
+        perm[b + 1] = perm[b];
+        --b;
+      }
+      perm[b + 1] = v;
+    }
+  }
+}
+
+// rank sort of long rows (positions are distinct, so ranks are a permutation): tmp[beg + rank] = value
+__global__ void csr_rank_big_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                                  const int32_t* __restrict__ big_rows, const int32_t* __restrict__ n_big,
+                                  int32_t* __restrict__ tmp) {
+  const int nb = *n_big;
+  for (int q = blockIdx.x; q < nb; q += gridDim.x) {
+    int r = big_rows[q];
+    int beg = rowptr[r], end = rowptr[r + 1];
+    for (int a = beg + threadIdx.x; a < end; a += blockDim.x) {
+      int v = perm[a];
+      int rank = 0;
+      for (int b = beg; b < end; ++b) rank += (perm[b] < v);
+      tmp[beg + rank] = v;
+    }
+  }
+}
+__global__ void csr_copy_big_rows(const int32_t* __restrict__ rowptr, int32_t* __restrict__ perm,
+                                  const int32_t* __restrict__ big_rows, const int32_t* __restrict__ n_big,
+                                  const int32_t* __restrict__ tmp) {
+  const int nb = *n_big;
+  for (int q = blockIdx.x; q < nb; q += gridDim.x) {
+    int r = big_rows[q];
+    int beg = rowptr[r], end = rowptr[r + 1];
+    for (int a = beg + threadIdx.x; a < end; a += blockDim.x) perm[a] = tmp[a];
+  }
+}
+
+__global__ void csr_gather_col(const int64_t* __restrict__ other, const int32_t* __restrict__ perm, int64_t n_items,
+                               int64_t n_rows, int32_t* __restrict__ col, int32_t* __restrict__ status) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_items;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = other[perm[k]];
+    bool ok = (v >= 0) & (v < n_rows);
+    col[k] = ok ? (int32_t)v : 0;
+    if (!ok && status) atomicOr(status, 1);
+  }
+}
+
+struct CsrWorkspace {
+  int32_t *cnt, *cursor, *chunk, *big_rows, *n_big, *tmp;
+  size_t bytes;
+};
+
+static CsrWorkspace carve(void* base, int64_t n_rows, int64_t n_items) {
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  int64_t n_chunks = ceil_div(n_rows + 1, kScanChunk);
+  size_t off = 0;
+  CsrWorkspace w;
+  char* p = static_cast<char*>(base);
+  w.cnt = reinterpret_cast<int32_t*>(p + off);      off += up(sizeof(int32_t) * (n_rows + 1));
+  w.cursor = reinterpret_cast<int32_t*>(p + off);   off += up(sizeof(int32_t) * (n_rows + 1));
+  w.n_big = reinterpret_cast<int32_t*>(p + off);    off += up(sizeof(int32_t) * 64);
+  // everything above is zero-initialised with ONE memset
+  w.chunk = reinterpret_cast<int32_t*>(p + off);    off += up(sizeof(int32_t) * (n_chunks + 1));
+  w.big_rows = reinterpret_cast<int32_t*>(p + off); off += up(sizeof(int32_t) * (n_items / kSmallRow + 1));
+  w.tmp = reinterpret_cast<int32_t*>(p + off);      off += up(sizeof(int32_t) * (n_items + 1));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace stinet
+
+using namespace stinet;
+
+extern "C" size_t stinet_csr_workspace_bytes(int64_t n_rows, int64_t n_items) {
+  if (n_rows < 0 || n_items < 0) return 0;
+  return carve(nullptr, n_rows, n_items).bytes;
+}
+
+extern "C" int stinet_csr_build(const int64_t* key, const int64_t* other, int64_t n_items, int64_t n_rows,
+                                int32_t* rowptr, int32_t* perm, int32_t* col, int32_t* key32, int32_t* status,
+                                void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(n_items >= 0 && n_rows >= 0, STINET_ERR_ARG, "csr_build: negative size");
+  STINET_REQUIRE(n_items < (int64_t(1) << 31) - 1 && n_rows < (int64_t(1) << 31) - 1, STINET_ERR_UNSUPPORTED,
+                 "csr_build: sizes must fit int32");
+  STINET_REQUIRE(rowptr && (n_items == 0 || (key && perm)), STINET_ERR_ARG, "csr_build: null pointer");
+  STINET_REQUIRE(!(other && !col), STINET_ERR_ARG, "csr_build: `other` given without `col`");
+  CsrWorkspace w = carve(workspace, n_rows, n_items);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "csr_build: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  size_t zero_bytes = reinterpret_cast<char*>(w.chunk) - reinterpret_cast<char*>(w.cnt);
+  cudaMemsetAsync(w.cnt, 0, zero_bytes, stream);
+  const int threads = 256;
+  const int grid_items = wave_grid(n_items, threads * 4, 8);
+  if (n_items > 0)
+    K(csr_count_kernel<<<grid_items, threads, 0, stream>>>(key, n_items, n_rows, w.cnt, key32, status));
+  const int n_chunks = (int)ceil_div(n_rows + 1, kScanChunk);
+  K(scan_chunk_sums<<<n_chunks, kScanThreads, 0, stream>>>(w.cnt, n_rows, w.chunk));
+  K(scan_chunk_offsets<<<1, kScanThreads, 0, stream>>>(w.chunk, n_chunks));
+  K(scan_write<<<n_chunks, kScanThreads, 0, stream>>>(w.cnt, n_rows, w.chunk, rowptr));
+  if (n_items > 0) {
+    K(csr_fill_kernel<<<grid_items, threads, 0, stream>>>(key, n_items, n_rows, rowptr, w.cursor, perm));
+    K(csr_sort_small_rows<<<wave_grid(n_rows, threads, 8), threads, 0, stream>>>(rowptr, n_rows, perm, w.big_rows,
+                                                                                 w.n_big));
+    K(csr_rank_big_rows<<<kSMs * 2, 256, 0, stream>>>(rowptr, perm, w.big_rows, w.n_big, w.tmp));
+    K(csr_copy_big_rows<<<kSMs * 2, 256, 0, stream>>>(rowptr, perm, w.big_rows, w.n_big, w.tmp));
+    if (other) K(csr_gather_col<<<grid_items, threads, 0, stream>>>(other, perm, n_items, n_rows, col, status));
+  }
+  return check_launch("csr_build");
+}

@@ -1,0 +1,289 @@
+// fp32 FFMA GEMM for the dense layers (exact-fp32 path: the 1e-5 parity bar rules out a single TF32/BF16 MMA pass).
+//   C[i,j] = sum_t A'(i,t) * B'(t,j), with each operand stored either t-contiguous or i/j-contiguous, which covers
+//   fwd   (A[M,K] W[N,K]^T),  dgrad (dC[M,N] W[N,K])  and  wgrad (dC[M,N]^T A[M,K], split over the row dimension
+//   with a fixed-order second-stage reduction -- deterministic, no atomics).
+// 128x64x16 tiles, 256 threads, 8x4 outputs per thread, register-staged double buffering.
+#include "common.cuh"
+
+namespace stinet {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kColsumRows = 1024;
+
+struct GemmArgs {
+  const float* A; int64_t lda;     // A'(i,t): A_TC ? A[i*lda+t] : A[t*lda+i]
+  const float* B; int64_t ldb;     // B'(t,j): B_TC ? B[j*ldb+t] : B[t*ldb+j]
+  float* C; int64_t ldc;           // C[i*ldc+j]  (or split partial s: C + s*I*J, ldc = J)
+  const float* bias; const int32_t* rowmask;
+  int I, J, T;
+  int t_per_split;
+};
+
+template <bool A_TC, bool B_TC>
+__global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const int t_begin = blockIdx.z * g.t_per_split;
+  const int t_end = min(g.T, t_begin + g.t_per_split);
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+  // register staging: A tile = 2048 elems -> 8 per thread, B tile = 1024 -> 4 per thread
+  float ra[8], rb[4];
+  const bool a_vec = ((g.lda & 3) == 0) && aligned16(g.A);
+  const bool b_vec = ((g.ldb & 3) == 0) && aligned16(g.B);
+
+  auto load_tiles = [&](int t0) {
+    // ---- A
+    if (A_TC) {
+      // (i,t): t fastest.  thread -> i = tid/4 + 64*r, t = (tid%4)*4 .. +3
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = i0 + (tid >> 2) + 64 * r;
+        const int t = t0 + (tid & 3) * 4;
+        const float* p = g.A + (int64_t)i * g.lda + t;
+        if (a_vec && i < g.I && t + 3 < t_end) {
+          float4 v = *reinterpret_cast<const float4*>(p);
+          ra[r * 4 + 0] = v.x; ra[r * 4 + 1] = v.y; ra[r * 4 + 2] = v.z; ra[r * 4 + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ra[r * 4 + q] = (i < g.I && t + q < t_end) ? p[q] : 0.f;
+        }
+      }
+    } else {
+      // (i,t): i fastest.  thread -> t = tid/32 + 8*r, i = (tid%32)*4 .. +3
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int t = t0 + (tid >> 5) + 8 * r;
+        const int i = i0 + (tid & 31) * 4;
+        const float* p = g.A + (int64_t)t * g.lda + i;
+        if (a_vec && t < t_end && i + 3 < g.I) {
+          float4 v = *reinterpret_cast<const float4*>(p);
+          ra[r * 4 + 0] = v.x; ra[r * 4 + 1] = v.y; ra[r * 4 + 2] = v.z; ra[r * 4 + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ra[r * 4 + q] = (t < t_end && i + q < g.I) ? p[q] : 0.f;
+        }
+      }
+    }
+    // ---- B
+    if (B_TC) {
+      // (t,j): t fastest.  thread -> j = tid/4, t = (tid%4)*4 .. +3
+      const int j = j0 + (tid >> 2);
+      const int t = t0 + (tid & 3) * 4;
+      const float* p = g.B + (int64_t)j * g.ldb + t;
+      if (b_vec && j < g.J && t + 3 < t_end) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rb[q] = (j < g.J && t + q < t_end) ? p[q] : 0.f;
+      }
+    } else {
+      // (t,j): j fastest.  thread -> t = tid/16, j = (tid%16)*4 .. +3
+      const int t = t0 + (tid >> 4);
+      const int j = j0 + (tid & 15) * 4;
+      const float* p = g.B + (int64_t)t * g.ldb + j;
+      if (b_vec && t < t_end && j + 3 < g.J) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rb[q] = (t < t_end && j + q < g.J) ? p[q] : 0.f;
+      }
+    }
+  };
+
+  auto store_tiles = [&](int buf) {
+    if (A_TC) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) As[buf][(tid & 3) * 4 + q][(tid >> 2) + 64 * r] = ra[r * 4 + q];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+        *reinterpret_cast<float4*>(&As[buf][(tid >> 5) + 8 * r][(tid & 31) * 4]) =
+            make_float4(ra[r * 4 + 0], ra[r * 4 + 1], ra[r * 4 + 2], ra[r * 4 + 3]);
+    }
+    if (B_TC) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) Bs[buf][(tid & 3) * 4 + q][tid >> 2] = rb[q];
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][tid >> 4][(tid & 15) * 4]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    }
+  };
+
+  int buf = 0;
+  if (t_begin < t_end) {
+    load_tiles(t_begin);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int t0 = t_begin; t0 < t_end; t0 += BK) {
+    const bool more = t0 + BK < t_end;
+    if (more) load_tiles(t0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+    }
+    if (more) store_tiles(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  float* C = g.C + (int64_t)blockIdx.z * g.I * (int64_t)g.ldc;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + ty * 8 + a;
+    if (i >= g.I) continue;
+    const bool add_bias = g.bias && (!g.rowmask || g.rowmask[i] > 0);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + tx * 4 + c;
+      if (j < g.J) C[(int64_t)i * g.ldc + j] = acc[a][c] + (add_bias ? g.bias[j] : 0.f);
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t IJ, int J,
+                                     float* __restrict__ out, int64_t ldo) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < IJ;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < splits; ++s) t += part[(int64_t)s * IJ + idx];
+    out[(idx / J) * ldo + (idx % J)] = t;
+  }
+}
+
+// partial[chunk][n] = sum over rows of the chunk of dC[m,n] * mask(m)
+__global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowmask,
+                                      int64_t M, int N, float* __restrict__ part) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t m0 = (int64_t)blockIdx.y * kColsumRows;
+  const int64_t m1 = min(M, m0 + kColsumRows);
+  float t = 0.f;
+  for (int64_t m = m0; m < m1; ++m)
+    if (!rowmask || rowmask[m] > 0) t += x[m * ldx + n];
+  part[(int64_t)blockIdx.y * N + n] = t;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * N + n];
+  out[n] = t;
+}
+
+static int pick_splits(int64_t I, int64_t J, int64_t T) {
+  int64_t tiles = ceil_div(I, BM) * ceil_div(J, BN);
+  int64_t want = ceil_div(2 * kSMs, tiles);
+  int64_t max_splits = ceil_div(T, BK * 16);
+  int64_t s = want < max_splits ? want : max_splits;
+  return (int)(s < 1 ? 1 : s);
+}
+
+struct GemmWs {
+  float *splitk, *colsum;
+  size_t bytes;
+};
+static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K) {
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  GemmWs w;
+  size_t sk = up(sizeof(float) * (size_t)pick_splits(N, K, M) * N * K);
+  size_t cs = up(sizeof(float) * (size_t)ceil_div(M > 0 ? M : 1, kColsumRows) * N);
+  char* p = static_cast<char*>(base);
+  w.splitk = reinterpret_cast<float*>(p);
+  w.colsum = reinterpret_cast<float*>(p + sk);
+  w.bytes = sk + cs;
+  return w;
+}
+
+}  // namespace stinet
+
+using namespace stinet;
+
+extern "C" size_t stinet_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision) {
+  (void)precision;
+  if (M < 0 || N <= 0 || K <= 0) return 0;
+  return carve_gemm(nullptr, M, N, K).bytes;
+}
+
+extern "C" int stinet_linear_fwd(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                                 const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                 int precision, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  (void)workspace; (void)workspace_bytes;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(A && W && C, STINET_ERR_ARG, "linear_fwd: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_fwd: bad shape");
+  STINET_REQUIRE(precision == STINET_PREC_FP32, STINET_ERR_UNSUPPORTED, "linear_fwd: precision %d not built", precision);
+  if (M == 0) return STINET_OK;
+  GemmArgs g{A, lda, W, ldw, C, ldc, bias, rowmask, (int)M, (int)N, (int)K, (int)K};
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
+  K(gemm_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g));
+  return check_launch("linear_fwd");
+}
+
+extern "C" int stinet_linear_dgrad(const float* dC, int64_t ldc, const float* W, int64_t ldw, float* dA, int64_t lda,
+                                   int64_t M, int64_t N, int64_t K, int precision, void* workspace,
+                                   size_t workspace_bytes, stinet_stream_t stream_) {
+  (void)workspace; (void)workspace_bytes;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(dC && W && dA, STINET_ERR_ARG, "linear_dgrad: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_dgrad: bad shape");
+  STINET_REQUIRE(precision == STINET_PREC_FP32, STINET_ERR_UNSUPPORTED, "linear_dgrad: precision %d not built", precision);
+  if (M == 0) return STINET_OK;
+  // dA[i=m, j=k] = sum_{t=n} dC[m,n] * W[n,k]
+  GemmArgs g{dC, ldc, W, ldw, dA, lda, nullptr, nullptr, (int)M, (int)K, (int)N, (int)N};
+  dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(M, BM), 1);
+  K(gemm_kernel<true, false><<<grid, kGemmThreads, 0, s>>>(g));
+  return check_launch("linear_dgrad");
+}
+
+extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t lda, const int32_t* rowmask,
+                                   float* dW, int64_t ldw, float* dbias, int64_t M, int64_t N, int64_t K,
+                                   int precision, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(dC && A && dW, STINET_ERR_ARG, "linear_wgrad: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_wgrad: bad shape");
+  STINET_REQUIRE(precision == STINET_PREC_FP32, STINET_ERR_UNSUPPORTED, "linear_wgrad: precision %d not built", precision);
+  GemmWs w = carve_gemm(workspace, M, N, K);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_wgrad: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  // dW[i=n, j=k] = sum_{t=m} dC[m,n] * A[m,k]
+  const int splits = pick_splits(N, K, M);
+  const int t_per = (int)(ceil_div(ceil_div(M > 0 ? M : 1, splits), BK) * BK);
+  dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(N, BM), (unsigned)splits);
+  if (splits == 1) {
+    GemmArgs g{dC, ldc, A, lda, dW, ldw, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
+    K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
+  } else {
+    GemmArgs g{dC, ldc, A, lda, w.splitk, K, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
+    K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
+    K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, splits, N * K, (int)K, dW, ldw));
+  }
+  if (dbias) {
+    const int chunks = (int)ceil_div(M > 0 ? M : 1, kColsumRows);
+    dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
+    K(colsum_partial_kernel<<<g2, 128, 0, s>>>(dC, ldc, rowmask, M, (int)N, w.colsum));
+    K(colsum_final_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, s>>>(w.colsum, chunks, (int)N, dbias));
+  }
+  return check_launch("linear_wgrad");
+}

@@ -1,0 +1,197 @@
+"""Device-side graph structure for one batch: CSR by target / by source for every edge set, cluster CSR for every
+trace map, per-level graph ids and norm segments.  Built once per batch by `stinet_csr_build` (no torch sort, no
+PyG), cached on the sample object, consumed by every kernel of the forward and backward pass.
+
+Replaces the COO `edge_index` / `trace` tensors that the reference hands to PyG's MessagePassing.propagate and to
+torch_scatter on every layer (reference models/surfacetextureinpaintingnet.py:398-471).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _abi
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise _abi.StinetError(f"{what} must live on a CUDA device (got {t.device}); stinet_b200 has no CPU path")
+
+
+def build_csr(key: torch.Tensor, other: Optional[torch.Tensor], n_rows: int, want_key32: bool = False,
+              status: Optional[torch.Tensor] = None):
+    """rowptr, perm, col, key32 (all int32) for positions grouped stably by `key`."""
+    _require_cuda(key, "index tensor")
+    assert key.dtype == torch.int64 and key.is_contiguous()
+    n_items = key.numel()
+    dev = key.device
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(n_items, dtype=torch.int32, device=dev)
+    col = torch.empty(n_items, dtype=torch.int32, device=dev) if other is not None else None
+    key32 = torch.empty(n_items, dtype=torch.int32, device=dev) if want_key32 else None
+    ws_bytes = _abi.query("stinet_csr_workspace_bytes", n_rows, n_items)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if other is not None:
+        assert other.dtype == torch.int64 and other.is_contiguous() and other.numel() == n_items
+    _abi.call("stinet_csr_build", key.data_ptr(), _ptr(other), n_items, n_rows, rowptr.data_ptr(), perm.data_ptr(),
+              _ptr(col), _ptr(key32), _ptr(status), ws.data_ptr(), ws_bytes, _stream(),
+              cost=(n_items * (16 + 8) + n_rows * 4, 0, ""))
+    return rowptr, perm, col, key32
+
+
+class EdgeCSR:
+    """One directed edge set (`edge_index[0]` = source j, `edge_index[1]` = target i) over n vertices."""
+
+    def __init__(self, edge_index: torch.Tensor, n: int, status: Optional[torch.Tensor] = None):
+        assert edge_index.dim() == 2 and edge_index.size(0) == 2
+        self.n, self.e = int(n), int(edge_index.size(1))
+        self._src = edge_index[0].contiguous()
+        self._dst = edge_index[1].contiguous()
+        self._status = status
+        # by target: row i lists its in-edges in original order; col_t = source vertex, eid_t = original edge id
+        self.rowptr_t, self.eid_t, self.col_t, _ = build_csr(self._dst, self._src, self.n, status=status)
+        self._by_source = None
+
+    def by_source(self):
+        """rowptr_s, col_s (= target vertex of each out-edge), eid_s -- only needed by backward passes."""
+        if self._by_source is None:
+            rowptr_s, eid_s, col_s, _ = build_csr(self._src, self._dst, self.n, status=self._status)
+            self._by_source = (rowptr_s, col_s, eid_s)
+        return self._by_source
+
+    @property
+    def degree(self) -> torch.Tensor:
+        """int32 in-degree per vertex (rowmask for the `isolated vertex -> 0` rule)."""
+        if not hasattr(self, "_deg"):
+            self._deg = (self.rowptr_t[1:] - self.rowptr_t[:-1]).contiguous()
+        return self._deg
+
+
+class ClusterCSR:
+    """One trace map: fine vertex i belongs to coarse vertex trace[i]."""
+
+    def __init__(self, trace: torch.Tensor, n_coarse: int, status: Optional[torch.Tensor] = None):
+        self.n_fine, self.n_coarse = int(trace.numel()), int(n_coarse)
+        self.rowptr, self.member, _, self.trace32 = build_csr(trace.contiguous(), None, self.n_coarse,
+                                                             want_key32=True, status=status)
+
+
+class Segments:
+    """Row partition used by the per-graph norm at one level (reference fastinstancenorm.py:51-60):
+    slice_ptr = linspace(0, N, B+1) (int), cnt = true per-graph vertex counts clamped to >= 1, gid = graph id per row.
+    `consistent` is True when the linspace slices coincide with the true graph boundaries."""
+
+    def __init__(self, n_rows: int, counts: Optional[List[int]], gid: Optional[torch.Tensor], device):
+        self.n_rows = int(n_rows)
+        if counts is None or len(counts) <= 1:
+            self.n_seg = 1
+            slice_ptr = [0, self.n_rows]
+            cnt = [max(self.n_rows, 1)]
+            self.gid = None
+            self.consistent = True
+        else:
+            self.n_seg = len(counts)
+            # same call as the reference (fastinstancenorm.py:53), evaluated on the host
+            slice_ptr = torch.linspace(0, self.n_rows, self.n_seg + 1, dtype=torch.int).tolist()
+            cnt = [max(int(c), 1) for c in counts]
+            true_ptr = [0]
+            for c in counts:
+                true_ptr.append(true_ptr[-1] + int(c))
+            self.consistent = (true_ptr == slice_ptr)
+            self.gid = gid
+        self.max_seg_rows = max(b - a for a, b in zip(slice_ptr[:-1], slice_ptr[1:]))
+        self.slice_ptr = torch.tensor(slice_ptr, dtype=torch.int32).to(device, non_blocking=True)
+        self.cnt = torch.tensor(cnt, dtype=torch.float32).to(device, non_blocking=True)
+
+
+class GraphCache:
+    """Everything structural the forward/backward of one batch needs.  `for_sample` memoises on the sample."""
+
+    def __init__(self, sample, n_levels: int):
+        x = sample.x
+        _require_cuda(x, "sample.x")
+        dev = x.device
+        self.device = dev
+        self.n_levels = n_levels
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        nv = sample.num_vertices
+        nv_host = nv.detach().to("cpu")            # the one host read of the step: [B, L+1] (or [L+1]) ints
+        if nv_host.dim() == 1:
+            nv_host = nv_host.unsqueeze(0)
+        self.per_graph = nv_host.tolist()          # [B][L+1]
+        self.batch_size = len(self.per_graph)
+        self.totals = [int(v) for v in nv_host.sum(dim=0).tolist()]
+        assert self.totals[0] == x.shape[0], "num_vertices[:,0] must sum to x.shape[0]"
+        self._sample = sample
+        self._edges: Dict[str, EdgeCSR] = {}
+        self._clusters: Dict[int, ClusterCSR] = {}
+        self._segments: Dict[tuple, Segments] = {}
+        self._gid: Dict[int, torch.Tensor] = {}
+
+    @staticmethod
+    def for_sample(sample, n_levels: int) -> "GraphCache":
+        c = getattr(sample, "_stinet_cache", None)
+        if c is None or c.n_levels != n_levels or c.device != sample.x.device:
+            c = GraphCache(sample, n_levels)
+            try:
+                object.__setattr__(sample, "_stinet_cache", c)
+            except Exception:
+                pass
+        return c
+
+    # -- structure ------------------------------------------------------------------------------------------
+    def edges(self, key: str, level: int) -> EdgeCSR:
+        if key not in self._edges:
+            ei = self._sample.edge_index if key == "edge_index" else self._sample[key]
+            self._edges[key] = EdgeCSR(ei, self.totals[level], self.status)
+        return self._edges[key]
+
+    def cluster(self, level: int) -> ClusterCSR:
+        """trace map level-1 -> level."""
+        if level not in self._clusters:
+            tr = self._sample[f"hierarchy_trace_index_{level}"]
+            assert tr.numel() == self.totals[level - 1]
+            self._clusters[level] = ClusterCSR(tr, self.totals[level], self.status)
+        return self._clusters[level]
+
+    def graph_id(self, level: int) -> Optional[torch.Tensor]:
+        """int32 graph id per vertex of `level`: level 0 from sample.batch, level l by max-pooling through the trace
+        (reference :422 `batch = scatter_max(batch, trace)`)."""
+        if self.batch_size <= 1:
+            return None
+        if level not in self._gid:
+            if level == 0:
+                self._gid[0] = self._sample.batch.to(torch.int32).contiguous()
+            else:
+                fine = self.graph_id(level - 1)
+                cl = self.cluster(level)
+                out = torch.empty(cl.n_coarse, dtype=torch.int32, device=self.device)
+                _abi.call("stinet_pool_max_i32", fine.data_ptr(), cl.rowptr.data_ptr(), cl.member.data_ptr(),
+                          cl.n_coarse, out.data_ptr(), _stream())
+                self._gid[level] = out
+        return self._gid[level]
+
+    def segments(self, level: int, per_graph: bool) -> Segments:
+        """per_graph=False: the whole batch is one instance (reference input/output blocks, :406-407, :459-460)."""
+        k = (level, per_graph and self.batch_size > 1)
+        if k not in self._segments:
+            if k[1]:
+                counts = [g[level] for g in self.per_graph]
+                self._segments[k] = Segments(self.totals[level], counts, self.graph_id(level), self.device)
+            else:
+                self._segments[k] = Segments(self.totals[level], None, None, self.device)
+        return self._segments[k]
+
+    def check_status(self) -> None:
+        """Synchronising validation of data-dependent errors (index out of range). Call from tests / debug."""
+        if int(self.status.item()) != 0:
+            raise _abi.StinetError("index tensor out of range for its level (status bit 0)")

@@ -1,0 +1,335 @@
+"""torch.autograd.Function wrappers around the C ABI (one per kernel family, explicit backward kernels).
+
+Every Function is stateless, deterministic and RNG-free, so it is re-entrant under torch.utils.checkpoint
+(reference models/surfacetextureinpaintingnet.py:429,438,451-455).  Tensors are borrowed as raw device pointers
+for the duration of the call; outputs and workspaces are allocated by torch's caching allocator on the caller's
+current stream.  fp32 storage everywhere; `precision` selects the arithmetic of the dense layers only.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _abi
+from ._abi import ACT_ELU, ACT_NONE, PREC, REDUCE
+from .graph import ClusterCSR, EdgeCSR, Segments, _ptr, _stream
+
+
+def _mat(t: torch.Tensor) -> torch.Tensor:
+    """fp32 CUDA matrix whose rows are contiguous (column slices of a wider buffer are fine)."""
+    if not t.is_cuda:
+        raise _abi.StinetError(f"stinet_b200 ops need CUDA tensors (got {t.device}); there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise _abi.StinetError(f"expected float32 storage, got {t.dtype}")
+    assert t.dim() == 2
+    if t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# dense layers
+
+
+class LinearFn(Function):
+    """y = x W^T + b, bias only on rows with rowmask > 0 when a rowmask is given."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, rowmask, precision):
+        x, weight = _mat(x), _mat(weight)
+        M, K = x.shape
+        N = weight.shape[0]
+        assert weight.shape[1] == K
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        prec = PREC[precision]
+        nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, prec)
+        ws = _ws(nb, x.device)
+        _abi.call("stinet_linear_fwd", x.data_ptr(), _ld(x), weight.data_ptr(), _ld(weight), _ptr(bias),
+                  _ptr(rowmask), y.data_ptr(), N, M, N, K, prec, ws.data_ptr(), nb, _stream(),
+                  cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+        ctx.save_for_backward(x, weight, rowmask)
+        ctx.has_bias = bias is not None
+        ctx.prec = prec
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight, rowmask = ctx.saved_tensors
+        dy = _mat(dy)
+        M, K = x.shape
+        N = weight.shape[0]
+        nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, ctx.prec)
+        ws = _ws(nb, x.device)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.float32, device=x.device)
+            _abi.call("stinet_linear_dgrad", dy.data_ptr(), _ld(dy), weight.data_ptr(), _ld(weight), dx.data_ptr(), K,
+                      M, N, K, ctx.prec, ws.data_ptr(), nb, _stream(),
+                      cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+            db = torch.empty((N,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            _abi.call("stinet_linear_wgrad", dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), _ptr(rowmask),
+                      dw.data_ptr(), K, _ptr(db), M, N, K, ctx.prec, ws.data_ptr(), nb, _stream(),
+                      cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+        return dx, dw, db, None, None
+
+
+def linear(x, weight, bias=None, rowmask=None, precision="fp32"):
+    return LinearFn.apply(x, weight, bias, rowmask, precision)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# message passing
+
+
+class EdgeMessageFn(Function):
+    """hid[i] = mean_{j->i} relu(P[i] + Q[j]),  PQ = [P | Q] of shape [N, 2H]."""
+
+    @staticmethod
+    def forward(ctx, pq, csr: EdgeCSR):
+        pq = _mat(pq)
+        n, h2 = pq.shape
+        h = h2 // 2
+        assert n == csr.n and h2 == 2 * h
+        hid = torch.empty((n, h), dtype=torch.float32, device=pq.device)
+        ld = _ld(pq)
+        _abi.call("stinet_edge_message_fwd", pq.data_ptr(), ld, pq.data_ptr() + 4 * h, ld, csr.rowptr_t.data_ptr(),
+                  csr.col_t.data_ptr(), n, h, hid.data_ptr(), h, _stream(),
+                  cost=(csr.e * (4 * h + 4) + n * (8 * h + 4), 2 * csr.e * h, f"H{h}"))
+        ctx.save_for_backward(pq)
+        ctx.csr = csr
+        return hid
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dhid):
+        (pq,) = ctx.saved_tensors
+        csr = ctx.csr
+        dhid = _mat(dhid)
+        n, h2 = pq.shape
+        h = h2 // 2
+        ld = _ld(pq)
+        dpq = torch.empty((n, h2), dtype=torch.float32, device=pq.device)
+        rowptr_s, col_s, _ = csr.by_source()
+        s = _stream()
+        _abi.call("stinet_edge_message_bwd_target", pq.data_ptr(), ld, pq.data_ptr() + 4 * h, ld, dhid.data_ptr(),
+                  _ld(dhid), csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h, dpq.data_ptr(), h2, s,
+                  cost=(csr.e * (4 * h + 4) + n * (12 * h + 4), 2 * csr.e * h, f"H{h}"))
+        _abi.call("stinet_edge_message_bwd_source", pq.data_ptr(), ld, pq.data_ptr() + 4 * h, ld, dhid.data_ptr(),
+                  _ld(dhid), csr.rowptr_t.data_ptr(), rowptr_s.data_ptr(), col_s.data_ptr(), n, h,
+                  dpq.data_ptr() + 4 * h, h2, s,
+                  cost=(csr.e * (8 * h + 8) + n * (8 * h + 4), 2 * csr.e * h, f"H{h}"))
+        return dpq, None
+
+
+def edge_message(pq, csr):
+    return EdgeMessageFn.apply(pq, csr)
+
+
+class AggregateFn(Function):
+    """out[i] = reduce_{j->i} x[j]  (mean / add / max over in-edges)."""
+
+    @staticmethod
+    def forward(ctx, x, csr: EdgeCSR, reduce: str):
+        x = _mat(x)
+        n, c = x.shape
+        assert n == csr.n
+        r = REDUCE[reduce]
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        arg = torch.empty((n, c), dtype=torch.int32, device=x.device) if r == 2 else None
+        _abi.call("stinet_aggregate_fwd", x.data_ptr(), _ld(x), csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(),
+                  csr.eid_t.data_ptr(), n, csr.e, c, r, out.data_ptr(), c, _ptr(arg), _stream(),
+                  cost=(csr.e * (4 * c + 4) + n * (4 * c + 4), csr.e * c, f"C{c}"))
+        ctx.csr, ctx.r, ctx.arg = csr, r, arg
+        if arg is not None:
+            ctx.mark_non_differentiable(arg)
+            return out, arg
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, *_):
+        csr = ctx.csr
+        g = _mat(g)
+        n, c = g.shape
+        rowptr_s, col_s, eid_s = csr.by_source()
+        dx = torch.empty((n, c), dtype=torch.float32, device=g.device)
+        _abi.call("stinet_aggregate_bwd", g.data_ptr(), _ld(g), rowptr_s.data_ptr(), col_s.data_ptr(),
+                  eid_s.data_ptr(), csr.rowptr_t.data_ptr(), _ptr(ctx.arg), n, c, ctx.r, dx.data_ptr(), c, _stream(),
+                  cost=(csr.e * (4 * c + 8) + n * (4 * c + 4), csr.e * c, f"C{c}"))
+        return dx, None, None
+
+
+def aggregate(x, csr, reduce="mean"):
+    return AggregateFn.apply(x, csr, reduce)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# pooling / unpooling
+
+
+class PoolMaxFn(Function):
+    @staticmethod
+    def forward(ctx, x, cl: ClusterCSR):
+        x = _mat(x)
+        n, c = x.shape
+        assert n == cl.n_fine
+        out = torch.empty((cl.n_coarse, c), dtype=torch.float32, device=x.device)
+        arg = torch.empty((cl.n_coarse, c), dtype=torch.int32, device=x.device)
+        _abi.call("stinet_pool_max_fwd", x.data_ptr(), _ld(x), cl.rowptr.data_ptr(), cl.member.data_ptr(), n,
+                  cl.n_coarse, c, out.data_ptr(), c, arg.data_ptr(), _stream(),
+                  cost=(n * (4 * c + 4) + cl.n_coarse * 8 * c, 0, f"C{c}"))
+        ctx.cl, ctx.arg = cl, arg
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _garg):
+        cl = ctx.cl
+        g = _mat(g)
+        c = g.shape[1]
+        dx = torch.empty((cl.n_fine, c), dtype=torch.float32, device=g.device)
+        _abi.call("stinet_pool_max_bwd", g.data_ptr(), _ld(g), ctx.arg.data_ptr(), cl.trace32.data_ptr(), cl.n_fine,
+                  c, dx.data_ptr(), c, _stream(), cost=(cl.n_coarse * 8 * c + cl.n_fine * (4 * c + 4), 0, f"C{c}"))
+        return dx, None
+
+
+class PoolMeanFn(Function):
+    @staticmethod
+    def forward(ctx, x, cl: ClusterCSR):
+        x = _mat(x)
+        n, c = x.shape
+        assert n == cl.n_fine
+        out = torch.empty((cl.n_coarse, c), dtype=torch.float32, device=x.device)
+        _abi.call("stinet_pool_mean_fwd", x.data_ptr(), _ld(x), cl.rowptr.data_ptr(), cl.member.data_ptr(),
+                  cl.n_coarse, c, out.data_ptr(), c, _stream(),
+                  cost=(n * (4 * c + 4) + cl.n_coarse * 4 * c, 0, f"C{c}"))
+        ctx.cl = cl
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        cl = ctx.cl
+        g = _mat(g)
+        c = g.shape[1]
+        dx = torch.empty((cl.n_fine, c), dtype=torch.float32, device=g.device)
+        _abi.call("stinet_pool_mean_bwd", g.data_ptr(), _ld(g), cl.rowptr.data_ptr(), cl.trace32.data_ptr(),
+                  cl.n_fine, c, dx.data_ptr(), c, _stream(),
+                  cost=(cl.n_coarse * 4 * c + cl.n_fine * (4 * c + 4), 0, f"C{c}"))
+        return dx, None
+
+
+class UnpoolFn(Function):
+    @staticmethod
+    def forward(ctx, xc, cl: ClusterCSR):
+        xc = _mat(xc)
+        nc, c = xc.shape
+        assert nc == cl.n_coarse
+        out = torch.empty((cl.n_fine, c), dtype=torch.float32, device=xc.device)
+        _abi.call("stinet_unpool_fwd", xc.data_ptr(), _ld(xc), cl.trace32.data_ptr(), cl.n_fine, c, out.data_ptr(), c,
+                  _stream(), cost=(cl.n_fine * (4 + 8 * c), 0, f"C{c}"))
+        ctx.cl = cl
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        cl = ctx.cl
+        g = _mat(g)
+        c = g.shape[1]
+        dxc = torch.empty((cl.n_coarse, c), dtype=torch.float32, device=g.device)
+        _abi.call("stinet_unpool_bwd", g.data_ptr(), _ld(g), cl.rowptr.data_ptr(), cl.member.data_ptr(), cl.n_coarse,
+                  c, dxc.data_ptr(), c, _stream(), cost=(cl.n_fine * (4 * c + 4) + cl.n_coarse * 4 * c, 0, f"C{c}"))
+        return dxc, None
+
+
+def pool_max(x, cl):
+    return PoolMaxFn.apply(x, cl)
+
+
+def pool_mean(x, cl):
+    return PoolMeanFn.apply(x, cl)
+
+
+def unpool(xc, cl):
+    return UnpoolFn.apply(xc, cl)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# per-graph instance norm fused with activation + residual
+
+
+class NormActResFn(Function):
+    """out = residual + act(instance_norm(x; segments))   (use_norm=False: identity norm)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, seg: Optional[Segments], use_norm: bool, act: int, eps: float):
+        x = _mat(x)
+        n, c = x.shape
+        dev = x.device
+        mean = rstd = ws = None
+        nb = 0
+        if use_norm:
+            assert seg is not None and seg.n_rows == n
+            mean = torch.empty((seg.n_seg, c), dtype=torch.float32, device=dev)
+            rstd = torch.empty((seg.n_seg, c), dtype=torch.float32, device=dev)
+            nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
+            ws = _ws(nb, dev)
+            _abi.call("stinet_segnorm_stats", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
+                      seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), _ptr(seg.gid), float(eps), mean.data_ptr(),
+                      rstd.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(8 * n * c, 3 * n * c, f"C{c}"))
+        res = _mat(residual) if residual is not None else None
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+        gid = seg.gid if (use_norm and seg is not None) else None
+        _abi.call("stinet_segnorm_apply", x.data_ptr(), _ld(x), n, c, _ptr(gid), _ptr(mean), _ptr(rstd), _ptr(res),
+                  _ld(res) if res is not None else 0, act, out.data_ptr(), c, _stream(),
+                  cost=(4 * n * c * (3 if res is not None else 2), 4 * n * c, f"C{c}"))
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.seg, ctx.use_norm, ctx.act, ctx.has_res = seg, use_norm, act, residual is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, mean, rstd = ctx.saved_tensors
+        seg = ctx.seg
+        dout = _mat(dout)
+        n, c = x.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+            if ctx.use_norm:
+                if not seg.consistent:
+                    raise _abi.StinetError(
+                        "instance-norm backward needs graphs of equal size in a batch: the reference's linspace slices "
+                        "(fastinstancenorm.py:53) do not match the true graph boundaries here")
+                nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
+                ws = _ws(nb, x.device)
+                _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, seg.n_seg,
+                          seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), _ptr(seg.gid),
+                          mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, ws.data_ptr(), nb, _stream(),
+                          cost=(20 * n * c, 10 * n * c, f"C{c}"))
+            else:
+                _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, 1, n, None,
+                          None, None, None, None, ctx.act, dx.data_ptr(), c, None, 0, _stream())
+        dres = dout if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        return dx, dres, None, None, None, None
+
+
+def norm_act_res(x, residual, seg, use_norm=True, act=ACT_ELU, eps=1e-5):
+    return NormActResFn.apply(x, residual, seg, use_norm, act, eps)

@@ -1,0 +1,248 @@
+"""Per-kernel parity on the B200: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+Integer / index work is bit-exact; fp32 within 1e-5 relative (||a-b||inf / ||b||inf per tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import stinet_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def _graph(kind):
+    from stinet_b200 import synthetic
+    if kind == "ico":
+        s = synthetic.icosphere_sample(4, 2, seed=11, mask_radius=3)
+        return s.edge_index, s.num_nodes
+    if kind == "grid_shuffled":
+        s = synthetic.grid_sample(32, 1, seed=5)
+        return s.edge_index, s.num_nodes
+    if kind == "graph18_isolated":
+        return synthetic.paper_graph18()
+    if kind == "dilated_asym":
+        s = synthetic.icosphere_sample(3, 2, seed=12, mask_radius=3, dilations=(2,))
+        return s["hierarchy_dil_2_edge_index_2"], int(s.num_vertices[2])
+    if kind == "multi_edges":       # duplicates + self loops + a hub: nothing the builder may assume away
+        g = torch.Generator().manual_seed(0)
+        e = torch.randint(0, 40, (2, 600), generator=g)
+        e[1, :200] = 7               # hub with in-degree > 64 exercises the long-row sort
+        return e, 41
+    if kind == "empty":
+        return torch.zeros((2, 0), dtype=torch.int64), 5
+    raise KeyError(kind)
+
+
+KINDS = ["ico", "grid_shuffled", "graph18_isolated", "dilated_asym", "multi_edges", "empty"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_csr_build_bit_exact(kind):
+    from stinet_b200.graph import EdgeCSR
+    ei, n = _graph(kind)
+    csr = EdgeCSR(ei.to(DEV), n)
+    rp, perm = O.csr_by_key(ei[1], n)
+    assert torch.equal(csr.rowptr_t.cpu(), rp)
+    assert torch.equal(csr.eid_t.cpu(), perm)
+    assert torch.equal(csr.col_t.cpu(), ei[0][perm.long()].to(torch.int32))
+    rs, cs, es = csr.by_source()
+    rp2, perm2 = O.csr_by_key(ei[0], n)
+    assert torch.equal(rs.cpu(), rp2) and torch.equal(es.cpu(), perm2)
+    assert torch.equal(cs.cpu(), ei[1][perm2.long()].to(torch.int32))
+
+
+def test_csr_flags_out_of_range_index():
+    from stinet_b200.graph import EdgeCSR
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ei = torch.tensor([[0, 1, 2], [1, 9, 0]])
+    EdgeCSR(ei.to(DEV), 3, status)
+    assert int(status.item()) == 1
+
+
+@pytest.mark.parametrize("kind", ["ico", "graph18_isolated", "dilated_asym", "multi_edges"])
+@pytest.mark.parametrize("reduce", ["mean", "add", "max"])
+@pytest.mark.parametrize("c", [3, 16, 128])
+def test_aggregate_fwd_bwd(kind, reduce, c):
+    from stinet_b200 import ops
+    from stinet_b200.graph import EdgeCSR
+    ei, n = _graph(kind)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, c, generator=g)
+    if reduce == "max":
+        x = torch.round(x * 2) / 2          # many exact ties: the first-edge-wins rule must match bit for bit
+    go = torch.randn(n, c, generator=g)
+    xr = x.clone().requires_grad_(True)
+    msg = xr.index_select(0, ei[0])
+    if reduce == "max":
+        ref, ref_arg = O.scatter_max(msg, ei[1], n)
+    else:
+        ref = O.aggregate(msg, ei[1], n, reduce)
+    ref.backward(go)
+    xd = x.to(DEV).requires_grad_(True)
+    csr = EdgeCSR(ei.to(DEV), n)
+    out = ops.aggregate(xd, csr, reduce)
+    if reduce == "max":
+        out, arg = out
+        assert torch.equal(arg.cpu().long(), ref_arg)
+        assert torch.equal(out.cpu(), ref.detach())
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["ico", "graph18_isolated", "dilated_asym", "multi_edges", "grid_shuffled"])
+@pytest.mark.parametrize("din,dout,trans_inv", [(10, 8, True), (4, 8, False), (64, 64, False), (32, 100, False)])
+def test_edge_conv_vs_literal_per_edge_mlp(kind, din, dout, trans_inv):
+    """Hoisted, fused CUDA EdgeConv == the reference's per-edge MLP + scatter-mean (values and all gradients)."""
+    from stinet_b200.models.modules import edge_conv_filter, edge_conv_translation_invariance
+    ei, n = _graph(kind)
+    torch.manual_seed(2)
+    module = edge_conv_translation_invariance.EdgeConvTransInv if trans_inv else None
+    conv = edge_conv_filter.get_gcn_filter(din, dout, module=module, double_input=not trans_inv)
+    with torch.no_grad():
+        for p in conv.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.5)       # non-zero biases: isolated vertices must still output exactly 0
+    x = torch.randn(n, din)
+    go = torch.randn(n, dout)
+    xr = x.clone().requires_grad_(True)
+    ref = O.edge_conv(xr, ei, conv.nn, "mean", trans_inv)
+    ref.backward(go)
+    ref_grads = {k: p.grad.clone() for k, p in conv.named_parameters()}
+    conv.zero_grad()
+    conv = conv.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out = conv(xd, ei.to(DEV))
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= TOL
+    for k, p in conv.named_parameters():
+        assert rel_err(p.grad, ref_grads[k]) <= TOL, k
+    deg = torch.bincount(ei[1], minlength=n)
+    if (deg == 0).any():
+        assert float(out[(deg == 0).to(DEV)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("c", [3, 64, 256])
+@pytest.mark.parametrize("pool", ["max", "mean"])
+def test_pool_unpool(c, pool):
+    from stinet_b200 import ops, synthetic
+    from stinet_b200.graph import ClusterCSR
+    s = synthetic.icosphere_sample(4, 1, seed=3, mask_radius=2)
+    trace = s["hierarchy_trace_index_1"]
+    nf, nc = trace.numel(), int(s.num_vertices[1]) + 2          # two EMPTY clusters at the end (dim_size > max+1)
+    g = torch.Generator().manual_seed(4)
+    x = torch.round(torch.randn(nf, c, generator=g) * 2) / 2     # ties
+    go = torch.randn(nc, c, generator=g)
+    xr = x.clone().requires_grad_(True)
+    if pool == "max":
+        ref, ref_arg = O.scatter_max(xr, trace, nc)
+    else:
+        ref = O.scatter_mean(xr, trace, nc)
+    ref.backward(go)
+    cl = ClusterCSR(trace.to(DEV), nc)
+    rp, member = O.csr_by_key(trace, nc)
+    assert torch.equal(cl.rowptr.cpu(), rp) and torch.equal(cl.member.cpu(), member)
+    assert torch.equal(cl.trace32.cpu().long(), trace)
+    xd = x.to(DEV).requires_grad_(True)
+    if pool == "max":
+        out, arg = ops.pool_max(xd, cl)
+        assert torch.equal(arg.cpu().long(), ref_arg)             # lowest fine id wins; empty -> n_fine sentinel
+        assert torch.equal(out.cpu(), ref.detach())
+    else:
+        out = ops.pool_mean(xd, cl)
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= TOL and rel_err(xd.grad, xr.grad) <= TOL
+    # unpool = gather; backward = segmented add
+    xc = torch.randn(nc, c, generator=g)
+    gf = torch.randn(nf, c, generator=g)
+    xcr = xc.clone().requires_grad_(True)
+    xcr[trace].backward(gf)
+    xcd = xc.to(DEV).requires_grad_(True)
+    up = ops.unpool(xcd, cl)
+    up.backward(gf.to(DEV))
+    assert torch.equal(up.cpu(), xc[trace])
+    assert rel_err(xcd.grad, xcr.grad) <= TOL
+
+
+def test_graph_id_pooling_int():
+    from stinet_b200 import synthetic
+    from stinet_b200.graph import GraphCache
+    b = synthetic.make_batch("icosphere", 3, 2, subdiv=3, mask_radius=2)
+    cache = GraphCache.for_sample(b.to(DEV), 2)
+    gid = b.batch
+    for lvl in (1, 2):
+        gid = O.scatter_max(gid, b[f"hierarchy_trace_index_{lvl}"], cache.totals[lvl])[0]
+        assert torch.equal(cache.graph_id(lvl).cpu().long(), gid)
+    cache.check_status()
+
+
+@pytest.mark.parametrize("c", [3, 64, 192])
+@pytest.mark.parametrize("layout", ["single", "equal", "ragged"])
+def test_instance_norm_elu_residual(c, layout):
+    from stinet_b200.models.modules import FastInstanceNorm
+    from stinet_b200._abi import ACT_ELU, StinetError
+    g = torch.Generator().manual_seed(5)
+    counts = {"single": [700], "equal": [300, 300, 300], "ragged": [500, 77, 323]}[layout]
+    n = sum(counts)
+    x = torch.randn(n, c, generator=g) * 3 + 1.5
+    res = torch.randn(n, c, generator=g)
+    go = torch.randn(n, c, generator=g)
+    batch = None if layout == "single" else torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts))
+    xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    ref = rr + torch.nn.functional.elu(O.fast_instance_norm(xr, batch))
+    ref.backward(go)
+    norm = FastInstanceNorm(c)
+    xd, rd = x.to(DEV).requires_grad_(True), res.to(DEV).requires_grad_(True)
+    out = norm(xd, None if batch is None else batch.to(DEV), rd, ACT_ELU)
+    assert rel_err(out, ref) <= TOL
+    if layout == "ragged":
+        with pytest.raises(StinetError):            # documented deviation: backward needs equal-size graphs
+            out.backward(go.to(DEV))
+        return
+    out.backward(go.to(DEV))
+    assert rel_err(xd.grad, xr.grad) <= TOL
+    assert torch.equal(rd.grad.cpu(), go)
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 16, 10), (777, 128, 64), (130, 3, 64), (4097, 256, 20), (64, 512, 256), (5, 8, 4)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_linear_fwd_dgrad_wgrad(m, n, k, masked):
+    from stinet_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k ** 0.5
+    b = torch.randn(n, generator=g)
+    go = torch.randn(m, n, generator=g)
+    mask = (torch.rand(m, generator=g) > 0.3).to(torch.int32) if masked else None
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = xr @ wr.t() + (br * mask.double().unsqueeze(1) if masked else br)
+    ref.backward(go.double())
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    out = ops.linear(xd, wd, bd, mask.to(DEV) if masked else None, "fp32")
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= TOL
+    assert rel_err(wd.grad, wr.grad) <= TOL
+    assert rel_err(bd.grad, br.grad) <= TOL
+
+
+def test_kernels_are_bitwise_deterministic():
+    """run-twice bit comparison (the reference's atomics are not deterministic; ours must be)."""
+    from stinet_b200.models.modules import edge_conv_filter
+    ei, n = _graph("ico")
+    torch.manual_seed(8)
+    conv = edge_conv_filter.get_gcn_filter(16, 32).to(DEV)
+    x = torch.randn(n, 16, device=DEV)
+    outs = []
+    for _ in range(2):
+        xd = x.clone().requires_grad_(True)
+        conv.zero_grad()
+        o = conv(xd, ei.to(DEV))
+        o.square().sum().backward()
+        outs.append((o.detach().clone(), xd.grad.clone(), [p.grad.clone() for p in conv.parameters()]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(a, b)
