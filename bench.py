@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- STINet hot path (multi-level mesh U-Net forward + backward over batched mesh graphs) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl stinet|reference] [--workload cfg2] [--dtype fp32]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+metric  = level-0 mesh vertices per second for one training step (graph-structure build + forward + masked-L1 loss +
+          backward [+ gradient all-reduce when N>1] + Adam step), BASELINE.json `metric`, on BASELINE.json configs[1]:
+          8 x 40,962-vertex synthetic icosphere crops, 10 input channels, 4 trace-map levels, fp32.
+value   = whole-job throughput, inputs resident in HBM when the timed region starts (weak scaling: every rank owns
+          its own batch, value = total vertices / max-over-ranks device time).
+e2e     = same step through the public module API with HOST (pinned) inputs: H2D of the batch and a D2H read of the
+          loss inside the timed region.
+roofline= the dominant kernel of the step (largest share of device time in a CUDA-event profile of the same step),
+          algorithmic bytes or flops per launch / its mean CUDA-event duration, against MEASURED_PEAKS.json.
+cpu_baseline / --impl reference = the CPU oracle port (oracle/stinet_oracle.py; PyG is not installable, so the
+          reference itself cannot run) on the host cores, on a bounded sample (ONE graph of the batch).
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "surface-texture-inpainting-net_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "cfg2": dict(kind="icosphere", gen=dict(subdiv=6), batch=8,
+                 net=dict(input_nc=10, output_nc=3, ngf=64, filter_type="edgeconvtransinv", norm="instance", n_blocks=9,
+                          n_levels=4, pooling_type="max", checkpoint_bottleneck=True),
+                 name="STINet 3D, synthetic icosphere crops 8 x 40,962 vertices, 10 ch, 4 trace-map levels, ngf 64, 9 blocks"),
+    # configs[0]: the reference's CPU-runnable 2D case (parity-test case, selectable for local runs)
+    "cfg1": dict(kind="grid", gen=dict(size=128), batch=4,
+                 net=dict(input_nc=4, output_nc=3, ngf=64, filter_type="edgeconv", norm="instance", n_blocks=9,
+                          n_levels=4, pooling_type="max"),
+                 name="STINet 2D, 4 x 128x128 image-grid graphs, 4 pool levels"),
+    "tiny": dict(kind="icosphere", gen=dict(subdiv=3, mask_radius=3), batch=2,
+                 net=dict(input_nc=10, output_nc=3, ngf=16, filter_type="edgeconvtransinv", norm="instance", n_blocks=2,
+                          n_levels=2, pooling_type="max"),
+                 name="tiny debug workload"),
+}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+def masked_l1(out, b):
+    """trainer glue that stays PyTorch: reference trainers/inpainting3d_trainer.py:127-137"""
+    composed = torch.where((b.mask > 0).expand_as(b.color), out, b.color)
+    loss = (composed - b.color).abs() * torch.pow(0.99, b.mask.squeeze().float()).unsqueeze(1)
+    return loss.mean()
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region through NVML in a background thread (the same
+    counters as the recipe's nvidia-smi line in B200_PROFILING.md, without forking nvidia-smi every 100 ms, which
+    stalls kernel launches)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period, self.samples, self.err = index, period_s, [], None
+        self._stop = threading.Event()
+        self.thread = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((mhz, rs, pw))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            self._stop.wait(self.period)
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        sm = sorted(m for m, _, _ in self.samples)
+        reasons = sorted(n for n, bit in self.REASONS.items() if any(r & bit for _, r, _ in self.samples))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "power_w_max": max((p for _, _, p in self.samples), default=None), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's algorithm for the path on the host cores.  torch_geometric / torch_scatter
+    cannot be installed in this image, so this is the CPU oracle port (kind='port'); each step is a bounded sample of
+    the workload: ONE graph of the batch, forward + loss + backward (recompute off)."""
+    if rank != 0:
+        return
+    from oracle import stinet_oracle as O
+    from stinet_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(49)
+    nk = {("norm_type" if k == "norm" else k): v for k, v in wl["net"].items()}
+    net = O.OracleSTINet(**nk)
+    b = synthetic.make_batch(wl["kind"], 1, wl["net"]["n_levels"], seed=49, **wl["gen"])
+    n0 = b.x.shape[0]
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        out = net(b)
+        O.masked_l1_loss(out, b).backward()
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    v = n0 / dt
+    sample = f"1 of {wl['batch']} graphs ({n0} vertices), fwd+loss+bwd, {steps} timed steps after {warm} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": "mesh vertices/sec fwd+bwd", "value": v, "unit": "vertices/s", "n_gpus": 0,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "vertices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def cpu_baseline(wl, budget_s=25.0):
+    from oracle import stinet_oracle as O
+    from stinet_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(49)
+    nk = {("norm_type" if k == "norm" else k): v for k, v in wl["net"].items()}
+    net = O.OracleSTINet(**nk)
+    b = synthetic.make_batch(wl["kind"], 1, wl["net"]["n_levels"], seed=49, **wl["gen"])
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        O.masked_l1_loss(net(b), b).backward()
+
+    t0 = time.perf_counter()
+    step()                                       # warm-up, also calibrates the budget
+    warm = time.perf_counter() - t0
+    n = max(1, min(5, int(budget_s / max(warm, 1e-3)) - 1))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return {"value": b.x.shape[0] / dt, "unit": "vertices/s", "cores": cores, "kind": "port",
+            "sample": f"CPU oracle port (PyG absent), 1 of {wl['batch']} graphs ({b.x.shape[0]} vertices), fwd+loss+bwd, "
+                      f"{n} timed steps after 1 warm-up, fp32, recompute off"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="stinet", choices=["stinet", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket timed region 1 with cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    from stinet_b200 import _abi, synthetic
+    from stinet_b200.models import surfacetextureinpaintingnet as S
+    from stinet_b200.parallel import GradAllReducer, init_distributed
+
+    rank, local, world = init_distributed()
+    assert torch.cuda.is_available(), "bench.py --impl stinet needs a CUDA device (there is no CPU fallback)"
+    assert _abi.load().stinet_device_ok() == 1, _abi.load().stinet_last_error().decode()
+    dev = torch.device("cuda", local)
+    W, K = max(args.warmup, 3), args.steps
+
+    torch.manual_seed(49)                                    # same initial weights on every rank
+    net = S.define_G(**wl["net"], gpu_ids=[dev], precision=args.dtype).train()
+    host = synthetic.make_batch(wl["kind"], wl["batch"], wl["net"]["n_levels"], seed=49 + 1000 * rank, **wl["gen"])
+    host = host.pin_memory()
+    n0 = int(host.x.shape[0])
+    resident = host.to(dev)
+    reducer = GradAllReducer(net)
+    opt = torch.optim.Adam(net.parameters(), lr=7e-5, amsgrad=True, fused=True)   # shipped 3D config :95-101
+
+    def step(b, read_loss=False):
+        b = copy.copy(b)
+        b.__dict__.pop("_stinet_cache", None)                # every step rebuilds the graph structure (new batch)
+        reducer.zero_grad()
+        loss = masked_l1(net(b), b)
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss.item() if read_loss else loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(W):
+        step(resident)
+    # ---- timed region 1: inputs resident in HBM -------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = _abi.query("stinet_launch_count")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.start()
+    e0.record()
+    for _ in range(K):
+        step(resident)
+    e1.record()
+    barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _abi.query("stinet_launch_count") - launches0
+    clk = clocks.stop() if rank == 0 else None
+    value = world * n0 * K / (ms * 1e-3)
+
+    # ---- timed region 2: end to end through the public API from pinned host memory ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step(host.to(dev, non_blocking=True), read_loss=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            step(host.to(dev, non_blocking=True), read_loss=True)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * n0 * K / (ms_e2e * 1e-3), "unit": "vertices/s",
+               "h2d_bytes_per_step": host.tensor_bytes(), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K}
+
+    # ---- roofline leg: CUDA-event profile of the same step (outside the timed regions) ----------------------------
+    pk, pk_src = peaks()
+    roofline, kernels = None, None
+    if rank == 0 and not args.no_profile:
+        with _abi.KernelProfiler() as prof:
+            for _ in range(2):
+                step(resident)
+        summ = prof.summary()
+        total = sum(r["ms"] for r in summ.values())
+        kernels = {k: {"calls_per_step": r["calls"] // 2, "ms_per_step": round(r["ms"] / 2, 4),
+                       "share": round(r["ms"] / total, 4),
+                       "GBps": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 else None,
+                       "TFLOPs": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 2) if r["ms"] > 0 else None}
+                   for k, r in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+        top, r = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        if top.startswith("linear"):
+            ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
+            peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": f"{pk_src} bf16 dense GEMM (sustained); this kernel runs the exact-fp32 FFMA path"}
+        else:
+            ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth"}
+        roofline["share_of_step"] = r["ms"] / total
+        roofline["ms_per_launch"] = r["ms"] / r["calls"]
+        # the dominant HBM-bound kernel is always reported too (north_star: aggregation / pool kernels vs HBM peak)
+        hbm = {k: v for k, v in summ.items() if not k.startswith("linear") and v["ms"] > 0}
+        if hbm:
+            k2, r2 = max(hbm.items(), key=lambda kv: kv[1]["ms"])
+            roofline["top_hbm_kernel"] = {"kernel": k2, "achieved_GBps": r2["bytes"] / (r2["ms"] * 1e-3) / 1e9,
+                                          "frac": r2["bytes"] / (r2["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                          "share_of_step": r2["ms"] / total}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(wl)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "mesh vertices/sec fwd+bwd", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "vertices_per_step_per_gpu": n0,
+                       "step": "graph-structure (CSR) build + forward + masked L1 + backward"
+                               + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam(amsgrad) step",
+                       "l2": "per-step working set (activations + weights, several GB) is far larger than the 126 MB L2; "
+                             "no explicit flush"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

