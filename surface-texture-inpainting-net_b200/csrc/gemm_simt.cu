@@ -9,7 +9,7 @@ namespace stinet {
 
 constexpr int BM = 128, BN = 64, BK = 16;
 constexpr int kGemmThreads = 256;
-constexpr int kColsumRows = 1024;
+constexpr int kColsumRows = 512;
 
 struct GemmArgs {
   const float* A; int64_t lda;     // A'(i,t): A_TC ? A[i*lda+t] : A[t*lda+i]
@@ -172,24 +172,63 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
   }
 }
 
-// partial[chunk][n] = sum over rows of the chunk of dC[m,n] * mask(m)
-__global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __restrict__ rowmask,
-                                      int64_t M, int N, float* __restrict__ part) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// dbias: masked column sums of dC in two deterministic stages.
+// stage 1: partial[chunk][n] = sum over the chunk's rows of dC[m,n] * mask(m); CTA = 32 column lanes x 8 row lanes,
+//          each column lane owns 4 (VEC) or 1 columns, rows are read as full 512 B / 128 B segments.
+template <bool VEC>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
+                                                             const int32_t* __restrict__ rowmask, int64_t M, int N,
+                                                             float* __restrict__ part) {
+  constexpr int W = VEC ? 4 : 1;
+  __shared__ float sm[8][32 * W + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * 32 + tx) * W;
   const int64_t m0 = (int64_t)blockIdx.y * kColsumRows;
   const int64_t m1 = min(M, m0 + kColsumRows);
-  float t = 0.f;
-  for (int64_t m = m0; m < m1; ++m)
-    if (!rowmask || rowmask[m] > 0) t += x[m * ldx + n];
-  part[(int64_t)blockIdx.y * N + n] = t;
+  float acc[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) acc[w] = 0.f;
+  if (n0 < N) {
+    for (int64_t m = m0 + ty; m < m1; m += 8) {
+      if (rowmask && rowmask[m] <= 0) continue;
+      if (VEC) {
+        const float4 v = *reinterpret_cast<const float4*>(x + m * ldx + n0);
+        acc[0] += v.x; acc[1 % W] += v.y; acc[2 % W] += v.z; acc[3 % W] += v.w;
+      } else {
+        acc[0] += x[m * ldx + n0];
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < W; ++w) sm[ty][tx * W + w] = acc[w];
+  __syncthreads();
+  if (ty == 0 && n0 < N) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += sm[y][tx * W + w];
+      if (n0 + w < N) part[(int64_t)blockIdx.y * N + n0 + w] = t;
+    }
+  }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// stage 2: out[n] = sum_chunks partial[chunk][n]; 32 column lanes x 32 chunk lanes, fixed-order tree over the lanes
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ part, int chunks, int N,
+                                                            float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
   float t = 0.f;
-  for (int c = 0; c < chunks; ++c) t += part[(int64_t)c * N + n];
-  out[n] = t;
+  if (n < N)
+    for (int c = ty; c < chunks; c += 32) t += part[(int64_t)c * N + n];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float r = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) r += sm[y][tx];
+    out[n] = r;
+  }
 }
 
 static int pick_splits(int64_t I, int64_t J, int64_t T) {
@@ -281,9 +320,15 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
   }
   if (dbias) {
     const int chunks = (int)ceil_div(M > 0 ? M : 1, kColsumRows);
-    dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
-    K(colsum_partial_kernel<<<g2, 128, 0, s>>>(dC, ldc, rowmask, M, (int)N, w.colsum));
-    K(colsum_final_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, s>>>(w.colsum, chunks, (int)N, dbias));
+    const bool vec = !(N & 3) && !(ldc & 3) && aligned16(dC);
+    if (vec) {
+      dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
+      K(colsum_partial_kernel<true><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, w.colsum));
+    } else {
+      dim3 g2((unsigned)ceil_div(N, 32), (unsigned)chunks);
+      K(colsum_partial_kernel<false><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, w.colsum));
+    }
+    K(colsum_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(w.colsum, chunks, (int)N, dbias));
   }
   return check_launch("linear_wgrad");
 }

@@ -100,20 +100,31 @@ __global__ void __launch_bounds__(kNormThreads) seg_colreduce_kernel(NormArgs a)
   }
 }
 
-// FIN: 0 -> out = sum/cnt ; 1 -> out = 1/sqrt(sum/cnt + eps)
+// FIN: 0 -> out = sum/cnt ; 1 -> out = 1/sqrt(sum/cnt + eps).  One CTA per (32 channels, segment): 32 channel lanes x
+// 32 chunk lanes read the partials coalesced, then a fixed-order sum over the chunk lanes (deterministic).
 template <int FIN>
-__global__ void seg_finalize_kernel(const float* __restrict__ part, const int32_t* __restrict__ slice_ptr,
-                                    const float* __restrict__ cnt, int n_seg, int channels, int max_chunks, float eps,
-                                    float* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_seg * channels) return;
-  const int s = idx / channels, c = idx % channels;
+__global__ void __launch_bounds__(1024)
+seg_finalize_kernel(const float* __restrict__ part, const int32_t* __restrict__ slice_ptr,
+                    const float* __restrict__ cnt, int n_seg, int channels, int max_chunks, float eps,
+                    float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int s = blockIdx.y;
+  const int c = blockIdx.x * 32 + tx;
   const int len = slice_ptr[s + 1] - slice_ptr[s];
   const int chunks = (len + kChunkRows - 1) / kChunkRows;
   float t = 0.f;
-  for (int k = 0; k < chunks; ++k) t += part[((int64_t)s * max_chunks + k) * channels + c];
-  const float m = t / cnt[s];
-  out[idx] = FIN == 0 ? m : 1.f / sqrtf(m + eps);
+  if (c < channels)
+    for (int k = ty; k < chunks; k += 32) t += part[((int64_t)s * max_chunks + k) * channels + c];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < channels) {
+    float r = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) r += sm[y][tx];
+    const float m = r / cnt[s];
+    out[(int64_t)s * channels + c] = FIN == 0 ? m : 1.f / sqrtf(m + eps);
+  }
 }
 
 template <bool VEC>
@@ -258,12 +269,12 @@ extern "C" int stinet_segnorm_stats(const float* x, int64_t ldx, int64_t n_rows,
                  workspace_bytes, w.bytes);
   const bool vec = nvec(channels, {x}, {ldx});
   NormArgs a{x, ldx, nullptr, 0, slice_ptr, gid, nullptr, nullptr, w.part0, w.part1, (int)channels, w.max_chunks, 0};
-  const int fin_grid = (int)ceil_div(n_seg * channels, 256);
+  const dim3 fin_grid((unsigned)ceil_div(channels, 32), (unsigned)n_seg);
   launch_colreduce<MODE_SUM>(vec, a, n_seg, s);
-  K(seg_finalize_kernel<0><<<fin_grid, 256, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, eps, mean));
+  K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, eps, mean));
   a.mean = mean;
   launch_colreduce<MODE_CSQ>(vec, a, n_seg, s);
-  K(seg_finalize_kernel<1><<<fin_grid, 256, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, eps, rstd));
+  K(seg_finalize_kernel<1><<<fin_grid, 1024, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, eps, rstd));
   return check_launch("segnorm_stats");
 }
 
@@ -301,9 +312,9 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
                    workspace_bytes, w.bytes);
     NormArgs a{x, ldx, dout, ldg, slice_ptr, gid, mean, rstd, w.part0, w.part1, (int)channels, w.max_chunks, act};
     launch_colreduce<MODE_BWD>(vec, a, n_seg, s);
-    const int fin_grid = (int)ceil_div(n_seg * channels, 256);
-    K(seg_finalize_kernel<0><<<fin_grid, 256, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s1));
-    K(seg_finalize_kernel<0><<<fin_grid, 256, 0, s>>>(w.part1, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s2));
+    const dim3 fin_grid((unsigned)ceil_div(channels, 32), (unsigned)n_seg);
+    K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s1));
+    K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.part1, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s2));
     s1 = w.s1;
     s2 = w.s2;
   }
