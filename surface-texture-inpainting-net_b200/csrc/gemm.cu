@@ -1,9 +1,13 @@
-// fp32 FFMA GEMM for the dense layers (exact-fp32 path: the 1e-5 parity bar rules out a single TF32/BF16 MMA pass).
+// Dense layers (nn.Linear fwd / dgrad / wgrad): entry points, planning and the exact-fp32 FFMA fallback.
 //   C[i,j] = sum_t A'(i,t) * B'(t,j), with each operand stored either t-contiguous or i/j-contiguous, which covers
 //   fwd   (A[M,K] W[N,K]^T),  dgrad (dC[M,N] W[N,K])  and  wgrad (dC[M,N]^T A[M,K], split over the row dimension
 //   with a fixed-order second-stage reduction -- deterministic, no atomics).
-// 128x64x16 tiles, 256 threads, 8x4 outputs per thread, register-staged double buffering.
+// Main path: the tcgen05/TMA kernel of gemm_tc.cu (3xTF32 for fp32 parity, or bf16 operands cast into the workspace).
+// Fallback for operands TMA cannot address (row pitch not a multiple of 16 B: the 10-channel input, the 3-channel
+// head): 128x64x16 FFMA tiles, 256 threads, 8x4 outputs per thread, register-staged double buffering.
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace stinet {
 
@@ -231,6 +235,27 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
   }
 }
 
+
+// fp32 -> bf16 cast of a row-major matrix (bf16 mode: the tensor-core kernel reads bf16 operands through TMA).
+// cols % 8 == 0, 16 B aligned rows on both sides; one thread converts 8 elements.
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
+                                                        __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  const int cpr = cols >> 3;
+  const int64_t total = rows * cpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cpr;
+    const int c = (int)(idx % cpr) << 3;
+    const float4 a = ld_stream(reinterpret_cast<const float4*>(x + r * ldx + c));
+    const float4 b = ld_stream(reinterpret_cast<const float4*>(x + r * ldx + c + 4));
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(y + r * ldy + c) = o;
+  }
+}
+
 static int pick_splits(int64_t I, int64_t J, int64_t T) {
   int64_t tiles = ceil_div(I, BM) * ceil_div(J, BN);
   int64_t want = ceil_div(2 * kSMs, tiles);
@@ -239,20 +264,62 @@ static int pick_splits(int64_t I, int64_t J, int64_t T) {
   return (int)(s < 1 ? 1 : s);
 }
 
+// split of the reduction dimension for the tensor-core wgrad: about two CTAs per SM, at least 256 rows per split,
+// whole 64-row k-blocks per split
+struct TcSplit { int splits; int64_t t_per; };
+static TcSplit tc_split(int64_t I, int64_t J, int64_t T) {
+  const int64_t bn = J <= 64 ? 64 : 128;
+  const int64_t tiles = ceil_div(I, 128) * ceil_div(J, bn);
+  int64_t want = ceil_div(2 * kSMs, tiles);
+  const int64_t cap = ceil_div(T, 256);
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  int64_t t_per = ceil_div(ceil_div(T, want), 64) * 64;
+  if (t_per < 64) t_per = 64;
+  return TcSplit{(int)ceil_div(T, t_per), t_per};
+}
+
+static int tc_mode(int precision) {
+  switch (precision) {
+    case STINET_PREC_FP32: return tc::MODE_TF32X3;
+    case STINET_PREC_BF16: return tc::MODE_BF16;
+    case STINET_PREC_TF32: return tc::MODE_TF32X1;
+    default: return -1;
+  }
+}
+static bool valid_precision(int p) { return p >= STINET_PREC_FP32 && p <= STINET_PREC_TF32; }
+
 struct GemmWs {
   float *splitk, *colsum;
+  __nv_bfloat16 *a16, *w16, *c16;
   size_t bytes;
 };
-static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K) {
+static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K, int precision) {
   auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
   GemmWs w;
-  size_t sk = up(sizeof(float) * (size_t)pick_splits(N, K, M) * N * K);
-  size_t cs = up(sizeof(float) * (size_t)ceil_div(M > 0 ? M : 1, kColsumRows) * N);
+  const int64_t rows = M > 0 ? M : 1;
+  int splits = pick_splits(N, K, rows);
+  const int tcs = tc_split(N, K, rows).splits;
+  if (tcs > splits) splits = tcs;
+  const size_t sk = up(sizeof(float) * (size_t)splits * N * K);
+  const size_t cs = up(sizeof(float) * (size_t)ceil_div(rows, kColsumRows) * N);
+  const bool b16 = precision == STINET_PREC_BF16;
+  const size_t a16 = b16 ? up(2 * (size_t)rows * K) : 0, w16 = b16 ? up(2 * (size_t)N * K) : 0,
+               c16 = b16 ? up(2 * (size_t)rows * N) : 0;
   char* p = static_cast<char*>(base);
   w.splitk = reinterpret_cast<float*>(p);
   w.colsum = reinterpret_cast<float*>(p + sk);
-  w.bytes = sk + cs;
+  w.a16 = reinterpret_cast<__nv_bfloat16*>(p + sk + cs);
+  w.w16 = reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16);
+  w.c16 = reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16 + w16);
+  w.bytes = sk + cs + a16 + w16 + c16;
   return w;
+}
+
+// fp32 matrix the cast kernel (and TMA) can address with 16-byte accesses
+static bool castable(const float* x, int64_t ld, int64_t cols) { return aligned16(x) && ld % 4 == 0 && cols % 8 == 0; }
+static void cast_bf16(const float* x, int64_t ld, int64_t rows, int64_t cols, __nv_bfloat16* y, cudaStream_t s) {
+  K(cast_bf16_kernel<<<wave_grid(rows * (cols / 8), 256, 8), 256, 0, s>>>(x, ld, rows, (int)cols, y, cols));
 }
 
 }  // namespace stinet
@@ -260,20 +327,35 @@ static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K) {
 using namespace stinet;
 
 extern "C" size_t stinet_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int precision) {
-  (void)precision;
   if (M < 0 || N <= 0 || K <= 0) return 0;
-  return carve_gemm(nullptr, M, N, K).bytes;
+  return carve_gemm(nullptr, M, N, K, precision).bytes;
 }
 
 extern "C" int stinet_linear_fwd(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                                  const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                                  int precision, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
-  (void)workspace; (void)workspace_bytes;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   STINET_REQUIRE(A && W && C, STINET_ERR_ARG, "linear_fwd: null pointer");
   STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_fwd: bad shape");
-  STINET_REQUIRE(precision == STINET_PREC_FP32, STINET_ERR_UNSUPPORTED, "linear_fwd: precision %d not built", precision);
+  STINET_REQUIRE(valid_precision(precision), STINET_ERR_ARG, "linear_fwd: unknown precision %d", precision);
   if (M == 0) return STINET_OK;
+  const int mode = tc_mode(precision);
+  if (mode >= 0) {
+    tc::Problem p{A, lda, false, W, ldw, false, C, ldc, bias, rowmask, M, N, K, 1, K, mode};
+    bool ok = true;
+    if (mode == tc::MODE_BF16) {
+      GemmWs w = carve_gemm(workspace, M, N, K, precision);
+      STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_fwd: workspace %zu < %zu",
+                     workspace_bytes, w.bytes);
+      ok = castable(A, lda, K) && castable(W, ldw, K);
+      if (ok) {
+        cast_bf16(A, lda, M, K, w.a16, s);
+        cast_bf16(W, ldw, N, K, w.w16, s);
+        p.A = w.a16; p.lda = K; p.B = w.w16; p.ldb = K;
+      }
+    }
+    if (ok && tc::eligible(p)) return tc::run(p, s);
+  }
   GemmArgs g{A, lda, W, ldw, C, ldc, bias, rowmask, (int)M, (int)N, (int)K, (int)K};
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
   K(gemm_kernel<true, true><<<grid, kGemmThreads, 0, s>>>(g));
@@ -283,13 +365,29 @@ extern "C" int stinet_linear_fwd(const float* A, int64_t lda, const float* W, in
 extern "C" int stinet_linear_dgrad(const float* dC, int64_t ldc, const float* W, int64_t ldw, float* dA, int64_t lda,
                                    int64_t M, int64_t N, int64_t K, int precision, void* workspace,
                                    size_t workspace_bytes, stinet_stream_t stream_) {
-  (void)workspace; (void)workspace_bytes;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   STINET_REQUIRE(dC && W && dA, STINET_ERR_ARG, "linear_dgrad: null pointer");
   STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_dgrad: bad shape");
-  STINET_REQUIRE(precision == STINET_PREC_FP32, STINET_ERR_UNSUPPORTED, "linear_dgrad: precision %d not built", precision);
+  STINET_REQUIRE(valid_precision(precision), STINET_ERR_ARG, "linear_dgrad: unknown precision %d", precision);
   if (M == 0) return STINET_OK;
   // dA[i=m, j=k] = sum_{t=n} dC[m,n] * W[n,k]
+  const int mode = tc_mode(precision);
+  if (mode >= 0) {
+    tc::Problem p{dC, ldc, false, W, ldw, true, dA, lda, nullptr, nullptr, M, K, N, 1, N, mode};
+    bool ok = true;
+    if (mode == tc::MODE_BF16) {
+      GemmWs w = carve_gemm(workspace, M, N, K, precision);
+      STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_dgrad: workspace %zu < %zu",
+                     workspace_bytes, w.bytes);
+      ok = castable(dC, ldc, N) && castable(W, ldw, K);
+      if (ok) {
+        cast_bf16(dC, ldc, M, N, w.c16, s);
+        cast_bf16(W, ldw, N, K, w.w16, s);
+        p.A = w.c16; p.lda = N; p.B = w.w16; p.ldb = K;
+      }
+    }
+    if (ok && tc::eligible(p)) return tc::run(p, s);
+  }
   GemmArgs g{dC, ldc, W, ldw, dA, lda, nullptr, nullptr, (int)M, (int)K, (int)N, (int)N};
   dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(M, BM), 1);
   K(gemm_kernel<true, false><<<grid, kGemmThreads, 0, s>>>(g));
@@ -302,21 +400,46 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   STINET_REQUIRE(dC && A && dW, STINET_ERR_ARG, "linear_wgrad: null pointer");
   STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_wgrad: bad shape");
-  STINET_REQUIRE(precision == STINET_PREC_FP32, STINET_ERR_UNSUPPORTED, "linear_wgrad: precision %d not built", precision);
-  GemmWs w = carve_gemm(workspace, M, N, K);
+  STINET_REQUIRE(valid_precision(precision), STINET_ERR_ARG, "linear_wgrad: unknown precision %d", precision);
+  GemmWs w = carve_gemm(workspace, M, N, K, precision);
   STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_wgrad: workspace %zu < %zu",
                  workspace_bytes, w.bytes);
   // dW[i=n, j=k] = sum_{t=m} dC[m,n] * A[m,k]
-  const int splits = pick_splits(N, K, M);
-  const int t_per = (int)(ceil_div(ceil_div(M > 0 ? M : 1, splits), BK) * BK);
-  dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(N, BM), (unsigned)splits);
-  if (splits == 1) {
-    GemmArgs g{dC, ldc, A, lda, dW, ldw, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
-    K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
-  } else {
-    GemmArgs g{dC, ldc, A, lda, w.splitk, K, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
-    K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
-    K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, splits, N * K, (int)K, dW, ldw));
+  bool done = false;
+  const int mode = tc_mode(precision);
+  if (mode >= 0 && M > 0) {
+    const TcSplit sp = tc_split(N, K, M);
+    tc::Problem p{dC, ldc, true, A, lda, true, sp.splits == 1 ? dW : w.splitk, sp.splits == 1 ? ldw : K,
+                  nullptr, nullptr, N, K, M, sp.splits, sp.t_per, mode};
+    bool ok = true;
+    if (mode == tc::MODE_BF16) {
+      ok = castable(dC, ldc, N) && castable(A, lda, K);
+      if (ok) {
+        cast_bf16(dC, ldc, M, N, w.c16, s);
+        cast_bf16(A, lda, M, K, w.a16, s);
+        p.A = w.c16; p.lda = N; p.B = w.a16; p.ldb = K;
+      }
+    }
+    if (ok && tc::eligible(p)) {
+      int rc = tc::run(p, s);
+      if (rc) return rc;
+      if (sp.splits > 1)
+        K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, N * K, (int)K, dW, ldw));
+      done = true;
+    }
+  }
+  if (!done) {
+    const int splits = pick_splits(N, K, M);
+    const int t_per = (int)(ceil_div(ceil_div(M > 0 ? M : 1, splits), BK) * BK);
+    dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(N, BM), (unsigned)splits);
+    if (splits == 1) {
+      GemmArgs g{dC, ldc, A, lda, dW, ldw, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
+      K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
+    } else {
+      GemmArgs g{dC, ldc, A, lda, w.splitk, K, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
+      K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
+      K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, splits, N * K, (int)K, dW, ldw));
+    }
   }
   if (dbias) {
     const int chunks = (int)ceil_div(M > 0 ? M : 1, kColsumRows);

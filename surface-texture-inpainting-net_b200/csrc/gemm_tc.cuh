@@ -1,0 +1,28 @@
+// Interface between the dense-layer entry points (gemm.cu) and the tcgen05 GEMM (gemm_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stinet {
+namespace tc {
+
+enum { MODE_TF32X3 = 0, MODE_TF32X1 = 1, MODE_BF16 = 2 };
+
+// C[i,j] = sum_t A'(i,t) B'(t,j);  a_mn: A'(i,t) = A[t*lda + i] (else A[i*lda + t]); same for B with j.
+// A and B are fp32 (TF32 modes) or bf16 (MODE_BF16); C is fp32.  With splits > 1, split z covers
+// t in [z*t_per_split, (z+1)*t_per_split) and writes its partial to C + z*I*ldc.
+struct Problem {
+  const void* A; int64_t lda; bool a_mn;
+  const void* B; int64_t ldb; bool b_mn;
+  float* C; int64_t ldc;
+  const float* bias; const int32_t* rowmask;
+  int64_t I, J, T;
+  int splits; int64_t t_per_split;
+  int mode;
+};
+
+bool eligible(const Problem& p);              // TMA alignment / size rules
+int run(const Problem& p, cudaStream_t s);    // STINET_OK or an error code (message via set_error)
+
+}  // namespace tc
+}  // namespace stinet

@@ -45,7 +45,7 @@ SIGNATURES = {
 }
 
 REDUCE = {"add": 0, "sum": 0, "mean": 1, "max": 2}
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "fp32_simt": 2, "tf32": 3}
 ACT_NONE, ACT_ELU = 0, 1
 
 
