@@ -57,11 +57,22 @@ class GraphBatch:
     def num_nodes(self) -> int:
         return int(self.x.shape[0])
 
+    def _host_num_vertices(self):
+        """[B][L+1] vertex counts as python ints, taken while `num_vertices` is still a host tensor, so the device
+        copy of the batch can be consumed without a device-to-host read."""
+        pre = self.__dict__.get("_nv_host")
+        nv = self.__dict__.get("num_vertices")
+        if pre is None and torch.is_tensor(nv) and not nv.is_cuda:
+            nv2 = nv if nv.dim() == 2 else nv.unsqueeze(0)
+            pre = tuple(tuple(int(x) for x in g) for g in nv2.tolist())
+        return pre
+
     def to(self, device, non_blocking: bool = False) -> "GraphBatch":
         out = GraphBatch()
         for k in self.keys:
             v = self.__dict__[k]
             out.__dict__[k] = v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v
+        out.__dict__["_nv_host"] = self._host_num_vertices()
         return out
 
     def pin_memory(self) -> "GraphBatch":
@@ -69,6 +80,7 @@ class GraphBatch:
         for k in self.keys:
             v = self.__dict__[k]
             out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) else v
+        out.__dict__["_nv_host"] = self._host_num_vertices()
         return out
 
     def tensor_bytes(self) -> int:

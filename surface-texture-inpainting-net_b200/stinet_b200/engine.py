@@ -1,0 +1,146 @@
+"""Whole-step CUDA-graph execution of the STINet hot path.
+
+One training step of the mesh U-Net is ~1000 kernel launches (graph-structure build, forward, loss, backward,
+optimizer), most of them short: launched one by one from Python the step is bound by launch overhead, not by the
+device.  `GraphedTrainStep` captures the whole step once per *batch shape* into a CUDA graph and replays it:
+
+    step = GraphedTrainStep(net, loss_fn, optimizer)
+    for batch in loader:                       # host (pinned) or device GraphBatch / PyG Batch
+        loss = step(batch)                     # H2D copies into the static inputs + one graph launch
+
+What is inside the graph: CSR / cluster-CSR construction from the batch's int64 `edge_index` / trace tensors (so
+every replay rebuilds the structure of the *new* batch on the device), forward, `loss_fn`, backward and
+`optimizer.step()`.  What must be equal between the captured batch and a replayed one is its *shape signature*:
+every tensor shape plus the per-graph, per-level vertex counts `num_vertices` (they size norm segments and grids).
+A batch with a new signature is captured on first use and cached; the reference's 2D trainer (equal-size image
+graphs) always hits one graph, the 3D trainer (variable crops) one graph per distinct crop topology.
+
+With more than one rank the gradient all-reduce runs between two graphs (forward+backward | optimizer), eagerly,
+on the same stream: the collective is a handful of launches and is not worth tying NCCL to graph capture.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import _abi
+from ._abi import StinetError
+from .data import GraphBatch
+
+
+def _tensor_items(batch):
+    keys = batch.keys() if callable(getattr(batch, "keys", None)) else batch.keys
+    for k in keys:
+        v = batch[k]
+        if torch.is_tensor(v):
+            yield k, v
+
+
+def batch_signature(batch) -> tuple:
+    """Hashable shape signature of a batch; reads `num_vertices` on the host (free for host batches)."""
+    shapes = tuple(sorted((k, tuple(v.shape), str(v.dtype)) for k, v in _tensor_items(batch)))
+    pre = getattr(batch, "_nv_host", None)      # GraphBatch keeps a host copy across .to(device)
+    if pre is not None:
+        return shapes, tuple(tuple(int(x) for x in g) for g in pre)
+    nv_host = batch.num_vertices.detach().to("cpu")
+    if nv_host.dim() == 1:
+        nv_host = nv_host.unsqueeze(0)
+    return shapes, tuple(tuple(int(x) for x in g) for g in nv_host.tolist())
+
+
+class _Captured:
+    __slots__ = ("static", "graph_a", "graph_b", "loss", "launches")
+
+
+class GraphedTrainStep:
+    """forward + loss + backward (+ all-reduce) + optimizer step, captured per batch signature and replayed."""
+
+    def __init__(self, net: torch.nn.Module, loss_fn: Callable, optimizer: Optional[torch.optim.Optimizer] = None,
+                 reducer=None, warmup: int = 2, max_cached: int = 8):
+        if optimizer is not None and not optimizer.defaults.get("capturable", False):
+            raise StinetError("GraphedTrainStep needs an optimizer created with capturable=True")
+        self.net, self.loss_fn, self.opt, self.reducer = net, loss_fn, optimizer, reducer
+        self.warmup, self.max_cached = max(int(warmup), 1), max_cached
+        self.world = reducer.world if reducer is not None else 1
+        self._cache: Dict[tuple, _Captured] = {}
+        self.captures = 0
+        self.replayed_launches = 0      # library kernels executed through graph replays (bench.py `gpu_launches`)
+
+    # ---- pieces of one step (run eagerly for warm-up, then under capture) -------------------------------------
+    def _fwd_bwd(self, static):
+        static.__dict__.pop("_stinet_cache", None)      # the structure is rebuilt from the batch's index tensors
+        if self.reducer is not None:
+            self.reducer.zero_grad()
+        elif self.opt is not None:
+            self.opt.zero_grad(set_to_none=True)
+        else:
+            self.net.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.net(static), static)
+        loss.backward()
+        return loss
+
+    def _finish(self):
+        if self.reducer is not None:
+            self.reducer.finish()
+
+    def _capture(self, batch, sig) -> _Captured:
+        dev = next(self.net.parameters()).device
+        c = _Captured()
+        c.static = GraphBatch()
+        for k, v in _tensor_items(batch):
+            c.static.__dict__[k] = v.to(dev, non_blocking=True).clone()
+        c.static.__dict__["_nv_host"] = sig[1]
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        overlap = getattr(self.reducer, "overlap", False)
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):                 # eager warm-up: lazy inits, allocator, segment tables
+                self._fwd_bwd(c.static)
+                self._finish()
+                if self.opt is not None:
+                    self.opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if self.reducer is not None:
+            self.reducer.overlap = False                 # hooks must not launch collectives inside the capture
+        n0 = _abi.query("stinet_launch_count")
+        try:
+            c.graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(c.graph_a):
+                c.loss = self._fwd_bwd(c.static)
+                if self.world == 1 and self.opt is not None:
+                    self.opt.step()
+            c.graph_b = None
+            if self.world > 1 and self.opt is not None:
+                c.graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(c.graph_b, pool=c.graph_a.pool()):
+                    self.opt.step()
+        finally:
+            if self.reducer is not None:
+                self.reducer.overlap = overlap
+        c.launches = _abi.query("stinet_launch_count") - n0   # kernels of this library recorded into the graphs
+        self.captures += 1
+        return c
+
+    def __call__(self, batch) -> torch.Tensor:
+        sig = batch_signature(batch)
+        c = self._cache.get(sig)
+        if c is None:
+            if len(self._cache) >= self.max_cached:
+                self._cache.pop(next(iter(self._cache)))
+            c = self._cache[sig] = self._capture(batch, sig)
+        for k, v in _tensor_items(batch):
+            c.static.__dict__[k].copy_(v, non_blocking=True)
+        c.graph_a.replay()
+        self.replayed_launches += c.launches
+        if c.graph_b is not None:
+            overlap = self.reducer.overlap
+            self.reducer.overlap = False
+            try:
+                self.reducer.finish()
+            finally:
+                self.reducer.overlap = overlap
+            c.graph_b.replay()
+        return c.loss

@@ -85,6 +85,22 @@ class ClusterCSR:
                                                              want_key32=True, status=status)
 
 
+_SEG_TABLES: Dict[tuple, tuple] = {}
+
+
+def _segment_tables(slice_ptr: tuple, cnt: tuple, device: torch.device):
+    """Device copies of the (host-derived) slice boundaries and divisors, memoised per (sizes, device): batches of
+    the same shape re-use them, so a step that is being captured into a CUDA graph performs no host-to-device copy."""
+    key = (slice_ptr, cnt, device)
+    hit = _SEG_TABLES.get(key)
+    if hit is None:
+        if len(_SEG_TABLES) > 4096:
+            _SEG_TABLES.clear()
+        hit = (torch.tensor(slice_ptr, dtype=torch.int32).to(device), torch.tensor(cnt, dtype=torch.float32).to(device))
+        _SEG_TABLES[key] = hit
+    return hit
+
+
 class Segments:
     """Row partition used by the per-graph norm at one level (reference fastinstancenorm.py:51-60):
     slice_ptr = linspace(0, N, B+1) (int), cnt = true per-graph vertex counts clamped to >= 1, gid = graph id per row.
@@ -109,8 +125,7 @@ class Segments:
             self.consistent = (true_ptr == slice_ptr)
             self.gid = gid
         self.max_seg_rows = max(b - a for a, b in zip(slice_ptr[:-1], slice_ptr[1:]))
-        self.slice_ptr = torch.tensor(slice_ptr, dtype=torch.int32).to(device, non_blocking=True)
-        self.cnt = torch.tensor(cnt, dtype=torch.float32).to(device, non_blocking=True)
+        self.slice_ptr, self.cnt = _segment_tables(tuple(slice_ptr), tuple(cnt), torch.device(device))
 
 
 class GraphCache:
@@ -123,13 +138,16 @@ class GraphCache:
         self.device = dev
         self.n_levels = n_levels
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        nv = sample.num_vertices
-        nv_host = nv.detach().to("cpu")            # the one host read of the step: [B, L+1] (or [L+1]) ints
-        if nv_host.dim() == 1:
-            nv_host = nv_host.unsqueeze(0)
-        self.per_graph = nv_host.tolist()          # [B][L+1]
+        pre = getattr(sample, "_nv_host", None)    # host copy supplied by the caller (engine.GraphedTrainStep)
+        if pre is not None:
+            self.per_graph = [list(map(int, g)) for g in pre]
+        else:
+            nv_host = sample.num_vertices.detach().to("cpu")   # the one host read of the step: [B, L+1] (or [L+1]) ints
+            if nv_host.dim() == 1:
+                nv_host = nv_host.unsqueeze(0)
+            self.per_graph = nv_host.tolist()      # [B][L+1]
         self.batch_size = len(self.per_graph)
-        self.totals = [int(v) for v in nv_host.sum(dim=0).tolist()]
+        self.totals = [sum(g[l] for g in self.per_graph) for l in range(len(self.per_graph[0]))]
         assert self.totals[0] == x.shape[0], "num_vertices[:,0] must sum to x.shape[0]"
         self._sample = sample
         self._edges: Dict[str, EdgeCSR] = {}

@@ -67,7 +67,7 @@ class GradAllReducer:
             self.buckets.append(flat)
             self._pending.append(len(group))
         self._sizes = list(self._pending)
-        if self.overlap:
+        if self.world > 1:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
 
@@ -78,6 +78,8 @@ class GradAllReducer:
         self._handles = []
 
     def _on_grad(self, p):
+        if not self.overlap:                       # e.g. while a step is being captured into a CUDA graph
+            return
         b = self._bucket_of[p]
         self._pending[b] -= 1
         if self._pending[b] == 0:
