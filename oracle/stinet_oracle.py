@@ -29,6 +29,90 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 # ------------------------------------------------------------------------------------------------
+# discrete decisions (ReLU signs of the message MLP, max-pool winners)
+
+
+class Decisions:
+    """The network is smooth except for its discrete choices: the sign of every message-MLP pre-activation (ReLU) and
+    the winner of every max-pool cluster.  Two correct evaluations in different precisions (fp32 vs fp64, CPU vs GPU,
+    the reference's own CPU and CUDA paths) take the same choices everywhere except where a pre-activation lies within
+    rounding distance of zero (or two cluster members within rounding distance of each other); there the derivative is
+    discontinuous and isolated gradient entries legitimately differ.  To compare gradients at 1e-5 anyway, the oracle
+    can be made to REPLAY the choices of the implementation under test:
+
+        with Decisions.replay(choices) as d:    # choices: list of ("relu", bool [E, 2*dout]) / ("pool", long [n_c, C])
+            out = oracle(batch)                 # in call order (input blocks, [pool, encoder block]*, bottleneck, ...)
+        d.max_relu_margin, d.max_pool_margin    # how far from the discontinuity the differing choices were, relative
+                                                # to the layer's largest pre-activation / feature (legitimacy check)
+
+    and `Decisions.record()` returns the oracle's own choices.  Outside a `with` block the oracle is unchanged."""
+
+    _active: Optional["Decisions"] = None
+
+    def __init__(self, choices=None):
+        self.choices = list(choices) if choices is not None else None
+        self.recorded: List[Tuple[str, torch.Tensor]] = []
+        self.pos = 0
+        self.max_relu_margin = 0.0
+        self.max_pool_margin = 0.0
+        self.n_relu_diff = 0
+        self.n_pool_diff = 0
+
+    @classmethod
+    def replay(cls, choices):
+        return cls(choices)
+
+    @classmethod
+    def record(cls):
+        return cls(None)
+
+    def __enter__(self):
+        Decisions._active = self
+        return self
+
+    def __exit__(self, *exc):
+        Decisions._active = None
+
+    def _next(self, kind):
+        k, v = self.choices[self.pos]
+        assert k == kind, f"decision stream out of step: expected {kind}, got {k} at {self.pos}"
+        self.pos += 1
+        return v
+
+    def relu(self, pre: torch.Tensor) -> torch.Tensor:
+        own = pre > 0
+        if self.choices is None:
+            self.recorded.append(("relu", own))
+            return F.relu(pre)
+        m = self._next("relu").to(pre.device)
+        diff = m != own
+        if bool(diff.any()):
+            self.n_relu_diff += int(diff.sum())
+            scale = float(pre.detach().abs().max())
+            self.max_relu_margin = max(self.max_relu_margin, float(pre.detach().abs()[diff].max()) / max(scale, 1e-30))
+        return pre * m.to(pre.dtype)
+
+    def pool_max(self, src: torch.Tensor, index: torch.Tensor, n: int):
+        out, arg = scatter_max(src, index, n)
+        if self.choices is None:
+            self.recorded.append(("pool", arg))
+            return out, arg
+        given = self._next("pool").to(torch.long)
+        n_src = src.size(0)
+        valid = given < n_src
+        picked = torch.where(valid, src.gather(0, given.clamp(max=max(n_src - 1, 0))), torch.zeros_like(out))
+        diff = given != arg
+        if bool(diff.any()):
+            self.n_pool_diff += int(diff.sum())
+            scale = float(src.detach().abs().max())
+            gap = (out.detach() - picked.detach()).abs()[diff].max()
+            self.max_pool_margin = max(self.max_pool_margin, float(gap) / max(scale, 1e-30))
+            # a replayed winner must still belong to the cluster it wins
+            assert bool((index[given[diff & valid]] == torch.nonzero(diff & valid)[:, 0]).all()), "winner outside cluster"
+        return picked, given
+
+
+# ------------------------------------------------------------------------------------------------
 # integer structure
 
 
@@ -125,7 +209,13 @@ def edge_conv(x, edge_index, mlp: nn.Module, aggr: str = "mean", trans_inv: bool
     x_j = x.index_select(0, edge_index[0])
     x_i = x.index_select(0, edge_index[1])
     inp = (x_j - x_i) if trans_inv else torch.cat([x_i, x_j - x_i], dim=-1)
-    return aggregate(mlp(inp), edge_index[1], x.size(0), aggr)
+    dec = Decisions._active
+    if dec is None:
+        msg = mlp(inp)
+    else:                                   # same arithmetic, the ReLU's sign choices recorded or replayed
+        assert len(mlp) == 3 and isinstance(mlp[1], nn.ReLU)
+        msg = mlp[2](dec.relu(mlp[0](inp)))
+    return aggregate(msg, edge_index[1], x.size(0), aggr)
 
 
 def sage_conv(x, edge_index, lin_l: nn.Linear, lin_r: nn.Linear, trans_inv: bool = False):
@@ -287,7 +377,8 @@ class OracleSTINet(nn.Module):
             if batch is not None:
                 batch = scatter_max(batch, trace, n_l)[0]           # :422
             if self.pooling_type == "max":
-                out, arg = scatter_max(out, trace, n_l)             # :386
+                dec = Decisions._active
+                out, arg = scatter_max(out, trace, n_l) if dec is None else dec.pool_max(out, trace, n_l)   # :386
                 inter[f"pool_arg_{lvl}"] = arg
             else:
                 out = scatter_mean(out, trace, n_l)                 # :384

@@ -20,6 +20,11 @@ SHAPES = [  # (M, N, K)
 ]
 
 
+SMALL = [(8192, 128, 4), (8192, 32, 64), (8192, 32, 4), (2048, 256, 128), (2048, 64, 128), (2048, 64, 32),
+         (512, 512, 128), (512, 128, 256), (7686, 32, 16), (7686, 16, 32), (1926, 128, 32), (486, 256, 64),
+         (8192, 64, 64), (8192, 32, 32), (126, 512, 128), (126, 128, 256)]
+
+
 def one(op, prec):
     import torch
     from stinet_b200 import _abi
@@ -28,7 +33,7 @@ def one(op, prec):
     p = PREC[prec]
     stream = torch.cuda.current_stream().cuda_stream
     out = []
-    for (M, N, K) in SHAPES:
+    for (M, N, K) in (SMALL if os.environ.get("GEMM_CHECK_SMALL") else SHAPES):
         g = torch.Generator(device="cpu").manual_seed(M + 7 * N + 13 * K)
         x = torch.randn(M, K, generator=g).to(dev)
         w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)

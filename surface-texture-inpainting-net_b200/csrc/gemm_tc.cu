@@ -4,13 +4,17 @@
 //
 // Each operand is either "K-major" (t contiguous in HBM:  A'(i,t) = A[i*ld + t]) or "MN-major" (i / j contiguous:
 // A'(i,t) = A[t*ld + i]); that covers  fwd (K,K),  dgrad (K,MN)  and  wgrad (MN,MN, split over t with a fixed-order
-// second-stage reduction done by the caller).  One CTA computes one 128 x BN output tile:
+// second-stage reduction done by the caller).  Persistent kernel: one CTA per SM walks the 128 x BN output tiles
+// (x reduction splits), 14 warps with fixed roles:
 //
-//   warp 0   : TMA producer   -- cp.async.bulk.tensor loads 128B-swizzled operand tiles into a kStages-deep smem ring
-//   warp 1   : MMA issuer     -- one elected thread issues tcgen05.mma (M=128, N=BN), accumulator in TMEM;
-//                                tcgen05.commit releases smem stages and finally signals the epilogue
-//   warps 2-5: (fp32 mode) in-smem operand split  x = hi + lo  (both rounded to TF32), then the epilogue:
-//              tcgen05.ld TMEM -> registers -> (+bias) -> global
+//   warp 0    : TMA producer  -- cp.async.bulk.tensor loads 128B-swizzled operand tiles into a kStages-deep smem ring
+//   warp 1    : MMA issuer    -- one elected thread issues tcgen05.mma (M=128, N=BN) into one of TWO TMEM accumulator
+//                                buffers; tcgen05.commit releases smem stages and hands finished buffers to the epilogue
+//   warps 2-5 : (fp32 mode) in-smem operand split  x = hi + lo  between the TMA and the MMA
+//   warps 6-13: epilogue      -- tcgen05.ld TMEM -> registers; in fp32 mode the partial sums of every 128 reduction
+//                                elements are added round-to-nearest into register accumulators (the tensor core's own
+//                                fp32 accumulation truncates); then (+bias) -> swizzled smem transpose -> coalesced
+//                                128-bit stores.  The epilogue of tile n overlaps the main loop of tile n+1.
 //
 // Arithmetic modes
 //   TF32X3 : fp32 storage, every product evaluated as  hi*hi + hi*lo + lo*hi  on kind::tf32 with fp32 accumulation --
@@ -19,6 +23,7 @@
 //   BF16   : bf16 storage (the caller casts), kind::f16 with fp32 accumulation -- the 2e-2 bar of the bf16 mode.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -26,8 +31,12 @@ namespace stinet {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int kThreads = 192;
+constexpr int kConvWarps = 4;                            // operand-split warps (fp32 mode)
+constexpr int kEpiWarps = 8;                             // epilogue warps: TMEM lane quarter = warp % 4, column half = (warp-6)/4
+constexpr int kEpiWarp0 = 2 + kConvWarps;
+constexpr int kThreads = 32 * (2 + kConvWarps + kEpiWarps);  // 448
 constexpr uint32_t kRowBytes = 128;  // one swizzle row: 32 fp32 or 64 bf16 along the contiguous dimension
+constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 32 * 4;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
 
 struct TcArgs {
   float* C;
@@ -36,6 +45,9 @@ struct TcArgs {
   const int32_t* rowmask;
   int I, J, T;
   int t_per_split;
+  int tiles_j, tiles_ij, n_units;  // work units = (split z, row tile, column tile), column tile fastest
+  int promote;                     // k-blocks accumulated in TMEM before the partial sum is promoted to registers
+  int split_acc;                   // fp32 mode: keep the hi*lo + lo*hi correction terms in their own TMEM accumulator
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -167,10 +179,16 @@ struct Cfg {
   static constexpr uint32_t kBBytes = BN * kRowBytes;
   static constexpr uint32_t kLoadBytes = kABytes + kBBytes;
   static constexpr uint32_t kStageBytes = (kSplit ? 2u : 1u) * kLoadBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr uint32_t kBarBytes = 8 * (3 * 8 + 4) + 16;
+  static constexpr int kStagesRaw = (227 * 1024 - 1024 - (int)kStagingBytes - (int)kBarBytes) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // BN is 64 / 128 / 256: already a power of two
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 8 * (3 * kStages + 1) + 16 + 1024;
+  // two accumulator buffers of BN columns; fp32 mode doubles that for the separate correction-term accumulators
+  static constexpr uint32_t kTmemCols = (kSplit ? 4 : 2) * BN;
+  static constexpr int kEpiCols = BN / 2;             // accumulator columns owned by one epilogue warp
+  // fp32 mode: the tensor core adds into its fp32 accumulator with truncation, so the error of a long reduction
+  // grows linearly with K (measured: ~5e-9 * K relative).  Every kPromote k-blocks (128 reduction elements) the
+  // partial sum is moved out of TMEM and added, round-to-nearest, to accumulators held in the epilogue warps' registers.
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
 };
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
@@ -183,29 +201,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  const uint32_t bar_base = base + kStages * C_::kStageBytes;
+  const uint32_t staging_off = kStages * C_::kStageBytes;
+  const uint32_t bar_base = base + staging_off + kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto conv_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  const uint32_t accum_bar = bar_base + 8u * (3 * kStages);
-  const uint32_t tmem_slot = accum_bar + 8u;
+  auto conv_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (24 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (26 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * 28;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * BN, i0 = blockIdx.y * BM;
-  const int t_begin = blockIdx.z * g.t_per_split;
-  const int t_end = min(g.T, t_begin + g.t_per_split);
-  const int nkb = (t_end - t_begin + C_::BKE - 1) / C_::BKE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 128);
+      mbar_init(conv_bar(s), 32 * kConvWarps);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
@@ -214,30 +233,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // decode of a work unit: split z, row tile, column tile -> origin of the output tile and the k-block range
+  struct Unit { int i0, j0, z, t_begin, nkb; };
+  auto decode = [&](int u) {
+    Unit w;
+    w.z = u / g.tiles_ij;
+    const int r = u - w.z * g.tiles_ij;
+    const int ti = r / g.tiles_j;
+    w.i0 = ti * BM;
+    w.j0 = (r - ti * g.tiles_j) * BN;
+    w.t_begin = w.z * g.t_per_split;
+    const int t_end = min(g.T, w.t_begin + g.t_per_split);
+    w.nkb = (t_end - w.t_begin + C_::BKE - 1) / C_::BKE;
+    return w;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), C_::kLoadBytes);
-        const int t0 = t_begin + kb * C_::BKE;
-        const uint32_t a_dst = base + s * C_::kStageBytes;
-        const uint32_t b_dst = a_dst + C_::kABytes;
-        if (!A_MN) {
-          tma_load_2d(a_dst, &tmA, t0, i0, full_bar(s));
-        } else {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+        const Unit w = decode(u);
+        for (int kb = 0; kb < w.nkb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), C_::kLoadBytes);
+          const int t0 = w.t_begin + kb * C_::BKE;
+          const uint32_t a_dst = base + s * C_::kStageBytes;
+          const uint32_t b_dst = a_dst + C_::kABytes;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, t0, w.i0, full_bar(s));
+          } else {
 #pragma unroll
-          for (int b = 0; b < BM / C_::MNE; ++b)
-            tma_load_2d(a_dst + b * (C_::BKE * kRowBytes), &tmA, i0 + b * C_::MNE, t0, full_bar(s));
-        }
-        if (!B_MN) {
-          tma_load_2d(b_dst, &tmB, t0, j0, full_bar(s));
-        } else {
+            for (int b = 0; b < BM / C_::MNE; ++b)
+              tma_load_2d(a_dst + b * (C_::BKE * kRowBytes), &tmA, w.i0 + b * C_::MNE, t0, full_bar(s));
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, t0, w.j0, full_bar(s));
+          } else {
 #pragma unroll
-          for (int b = 0; b < BN / C_::MNE; ++b)
-            tma_load_2d(b_dst + b * (C_::BKE * kRowBytes), &tmB, j0 + b * C_::MNE, t0, full_bar(s));
+            for (int b = 0; b < BN / C_::MNE; ++b)
+              tma_load_2d(b_dst + b * (C_::BKE * kRowBytes), &tmB, w.j0 + b * C_::MNE, t0, full_bar(s));
+          }
+          if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -253,94 +291,155 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t kMnLayout = kBf16 ? kLayoutSW128 : kLayoutSW128Base32;
       constexpr uint32_t kMnSbo = kBf16 ? 1024u : 512u;                    // bytes between k-groups inside one MMA
       constexpr uint32_t kMnKStep = C_::UMMA_K * kRowBytes;                // k rows consumed per MMA * 128 B
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(C_::kSplit ? conv_bar(s) : full_bar(s), ph);
-        tcgen05_fence_after();
-        const uint32_t a_hi = base + s * C_::kStageBytes;
-        const uint32_t b_hi = a_hi + C_::kABytes;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t acc_it = 0;
+      for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+        const Unit w = decode(u);
+        for (int kb0 = 0; kb0 < w.nkb; kb0 += g.promote) {
+          const int kb1 = min(w.nkb, kb0 + g.promote);
+          const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+          mbar_wait(tempty_bar(buf), aph ^ 1u);   // the epilogue has drained this accumulator buffer
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          const uint32_t tmem_s = g.split_acc ? tmem_d + 2 * BN : tmem_d;   // correction-term accumulator
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(C_::kSplit ? conv_bar(s) : full_bar(s), ph);
+            tcgen05_fence_after();
+            const uint32_t a_hi = base + s * C_::kStageBytes;
+            const uint32_t b_hi = a_hi + C_::kABytes;
 #pragma unroll
-        for (int k = 0; k < C_::BKE / C_::UMMA_K; ++k) {
-          const uint32_t a_off = A_MN ? k * kMnKStep : k * 32u;
-          const uint32_t b_off = B_MN ? k * kMnKStep : k * 32u;
-          auto adesc = [&](uint32_t addr) {
-            return A_MN ? make_smem_desc(addr + a_off, kMnAtomStride, kMnSbo, kMnLayout)
-                        : make_smem_desc(addr + a_off, 16u, 1024u, kLayoutSW128);
-          };
-          auto bdesc = [&](uint32_t addr) {
-            return B_MN ? make_smem_desc(addr + b_off, kMnAtomStride, kMnSbo, kMnLayout)
-                        : make_smem_desc(addr + b_off, 16u, 1024u, kLayoutSW128);
-          };
-          const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-          if (C_::kSplit) {
-            const uint32_t a_lo = a_hi + C_::kLoadBytes, b_lo = b_hi + C_::kLoadBytes;
-            umma<false>(tmem_base, adesc(a_lo), bdesc(b_hi), idesc, first);
-            umma<false>(tmem_base, adesc(a_hi), bdesc(b_lo), idesc, 1u);
-            umma<false>(tmem_base, adesc(a_hi), bdesc(b_hi), idesc, 1u);
-          } else {
-            umma<kBf16>(tmem_base, adesc(a_hi), bdesc(b_hi), idesc, first);
+            for (int k = 0; k < C_::BKE / C_::UMMA_K; ++k) {
+              const uint32_t a_off = A_MN ? k * kMnKStep : k * 32u;
+              const uint32_t b_off = B_MN ? k * kMnKStep : k * 32u;
+              auto adesc = [&](uint32_t addr) {
+                return A_MN ? make_smem_desc(addr + a_off, kMnAtomStride, kMnSbo, kMnLayout)
+                            : make_smem_desc(addr + a_off, 16u, 1024u, kLayoutSW128);
+              };
+              auto bdesc = [&](uint32_t addr) {
+                return B_MN ? make_smem_desc(addr + b_off, kMnAtomStride, kMnSbo, kMnLayout)
+                            : make_smem_desc(addr + b_off, 16u, 1024u, kLayoutSW128);
+              };
+              const uint32_t accumulate = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (C_::kSplit) {
+                const uint32_t a_lo = a_hi + C_::kLoadBytes, b_lo = b_hi + C_::kLoadBytes;
+                umma<false>(tmem_s, adesc(a_lo), bdesc(b_hi), idesc, accumulate);
+                umma<false>(tmem_s, adesc(a_hi), bdesc(b_lo), idesc, 1u);
+                umma<false>(tmem_d, adesc(a_hi), bdesc(b_hi), idesc, g.split_acc ? accumulate : 1u);
+              } else {
+                umma<kBf16>(tmem_d, adesc(a_hi), bdesc(b_hi), idesc, accumulate);
+              }
+            }
+            umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
+            if (++s == kStages) { s = 0; ph ^= 1u; }
           }
+          umma_commit(tfull_bar(buf));
+          ++acc_it;
         }
-        umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
       }
-      umma_commit(accum_bar);
+    }
+  } else if (warp < kEpiWarp0) {
+    // ===== operand split (fp32 mode): x = hi + lo, hi = x rounded to TF32 (written in place), lo = x - hi (exact in
+    // fp32; the tensor core keeps its top 11 significand bits).  Element-wise, so the swizzled layouts are untouched.
+    if (C_::kSplit) {
+      const int ct = threadIdx.x - 64;
+      constexpr int kChunks = C_::kLoadBytes / 16;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+        const Unit w = decode(u);
+        for (int kb = 0; kb < w.nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          uint4* hi = reinterpret_cast<uint4*>(base_ptr + (size_t)s * C_::kStageBytes);
+          uint4* lo = hi + kChunks;
+#pragma unroll 4
+          for (int idx = ct; idx < kChunks; idx += 32 * kConvWarps) {
+            const uint4 v = hi[idx];
+            uint4 h, l;
+            h.x = (v.x + 0x1000u) & 0xFFFFE000u; l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+            h.y = (v.y + 0x1000u) & 0xFFFFE000u; l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+            h.z = (v.z + 0x1000u) & 0xFFFFE000u; l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+            h.w = (v.w + 0x1000u) & 0xFFFFE000u; l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+            hi[idx] = h;
+            lo[idx] = l;
+          }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+          mbar_arrive(conv_bar(s));
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+      }
     }
   } else {
-    // ===== warps 2..5: operand split (fp32 mode), then epilogue =====
-    const int ct = threadIdx.x - 64;
-    if (C_::kSplit) {
-      constexpr int kChunks = C_::kLoadBytes / 16;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(full_bar(s), ph);
-        uint4* hi = reinterpret_cast<uint4*>(base_ptr + (size_t)s * C_::kStageBytes);
-        uint4* lo = hi + kChunks;
-#pragma unroll 4
-        for (int idx = ct; idx < kChunks; idx += 128) {
-          const uint4 v = hi[idx];
-          uint4 h, l;
-          h.x = to_tf32(__uint_as_float(v.x)); l.x = to_tf32(__uint_as_float(v.x) - __uint_as_float(h.x));
-          h.y = to_tf32(__uint_as_float(v.y)); l.y = to_tf32(__uint_as_float(v.y) - __uint_as_float(h.y));
-          h.z = to_tf32(__uint_as_float(v.z)); l.z = to_tf32(__uint_as_float(v.z) - __uint_as_float(h.z));
-          h.w = to_tf32(__uint_as_float(v.w)); l.w = to_tf32(__uint_as_float(v.w) - __uint_as_float(h.w));
-          hi[idx] = h;
-          lo[idx] = l;
-        }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
-        mbar_arrive(conv_bar(s));
-      }
-    }
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = i0 + q * 32 + lane;
-    const bool row_ok = row < g.I;
-    const bool add_bias = g.bias != nullptr && row_ok && (g.rowmask == nullptr || g.rowmask[row] > 0);
-    float* crow = g.C + (int64_t)blockIdx.z * g.I * g.ldc + (int64_t)row * g.ldc;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (row_ok) {
+    // ===== epilogue: TMEM -> registers (RN accumulation across promotion chunks) -> swizzled smem transpose ->
+    // coalesced 128-bit global stores =====
+    const int ew = warp - kEpiWarp0;
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int h = ew >> 2;             // column half
+    constexpr int EC = C_::kEpiCols;
+    float4* stage = reinterpret_cast<float4*>(base_ptr + staging_off + (size_t)ew * 4096);
+    float acc[EC];
+    uint32_t acc_it = 0;
+    for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+      const Unit w = decode(u);
+      for (int kb0 = 0; kb0 < w.nkb; kb0 += g.promote) {
+        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        mbar_wait(tfull_bar(buf), aph);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(h * EC);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const int j = j0 + c0 + c;
-          if (j < g.J) {
-            float4 v = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
-                                   __uint_as_float(r[c + 3]));
-            if (add_bias) {
-              const float4 b = *reinterpret_cast<const float4*>(g.bias + j);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            }
-            *reinterpret_cast<float4*>(crow + j) = v;
+        for (int cc = 0; cc < EC; cc += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + cc, r);
+          if (C_::kSplit && g.split_acc) {
+            uint32_t r2[32];
+            tmem_ld32(taddr + 2 * BN + cc, r2);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r2[c]));
+          }
+          if (kb0 == 0) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[cc + c] = __uint_as_float(r[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[cc + c] += __uint_as_float(r[c]);
           }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+        ++acc_it;
+      }
+      // ---- write the tile out
+      const int row = w.i0 + q * 32 + lane;                // the row this thread holds
+      const bool add_bias = g.bias != nullptr && row < g.I && (g.rowmask == nullptr || g.rowmask[row] > 0);
+      float* cbase = g.C + (int64_t)w.z * g.I * g.ldc;
+#pragma unroll
+      for (int cc = 0; cc < EC; cc += 32) {
+        const int jb = w.j0 + h * EC + cc;                 // first global column of this 32-column block
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 v = make_float4(acc[cc + 4 * c4], acc[cc + 4 * c4 + 1], acc[cc + 4 * c4 + 2], acc[cc + 4 * c4 + 3]);
+          if (add_bias && jb + 4 * c4 < g.J) {
+            const float4 b = *reinterpret_cast<const float4*>(g.bias + jb + 4 * c4);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          stage[lane * 8 + (c4 ^ (lane & 7))] = v;
+        }
+        __syncwarp();
+        const int c4r = lane & 7;
+        const int gcol = jb + 4 * c4r;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const float4 v = stage[rr * 8 + (c4r ^ (rr & 7))];
+          const int grow = w.i0 + q * 32 + rr;
+          if (grow < g.I && gcol < g.J) *reinterpret_cast<float4*>(cbase + (int64_t)grow * g.ldc + gcol) = v;
+        }
+        __syncwarp();
       }
     }
-    tcgen05_fence_before();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
@@ -406,8 +505,19 @@ static int launch(const Problem& p, cudaStream_t s) {
     STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split};
-  dim3 grid((unsigned)ceil_div(p.J, BN), (unsigned)ceil_div(p.I, BM), (unsigned)p.splits);
+  const int tiles_j = (int)ceil_div(p.J, BN), tiles_i = (int)ceil_div(p.I, BM);
+  const int64_t units = (int64_t)tiles_i * tiles_j * p.splits;
+  STINET_REQUIRE(units < (1ll << 31), STINET_ERR_UNSUPPORTED, "gemm_tc: too many tiles");
+  // fp32 mode: promote every 4 k-blocks (128 reduction elements) and keep the correction terms in their own
+  // accumulator.  Measured on B200 against fp64 (scripts/exp_promote.sh): 2.6e-7 .. 6.5e-7 max-norm relative error,
+  // independent of K and at no cost in time (FFMA tiles: 2.7e-7 .. 1.4e-6; one shared accumulator, no promotion: up
+  // to 3e-5 at K = 4096).  STINET_TC_PROMOTE / STINET_TC_SPLITACC override the two knobs for that experiment.
+  static const int env_promote = [] { const char* e = getenv("STINET_TC_PROMOTE"); return e ? atoi(e) : 4; }();
+  static const int env_split = [] { const char* e = getenv("STINET_TC_SPLITACC"); return e ? atoi(e) : 1; }();
+  TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split,
+           tiles_j, tiles_i * tiles_j, (int)units,
+           C_::kSplit ? (env_promote > 0 ? env_promote : 4) : (1 << 28), C_::kSplit ? env_split : 0};
+  const unsigned grid = (unsigned)(units < kSMs ? units : kSMs);   // persistent: one CTA per SM walks the work units
   K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, g));
   return check_launch("gemm_tc");
 }

@@ -157,8 +157,9 @@ class SurfaceTextureInpaintingNet(nn.Module):
         self.set_precision(precision)
 
     def set_precision(self, precision: str):
-        """'fp32' (exact, reference parity 1e-5) or 'bf16' (tcgen05 bf16 tiles, fp32 accumulate; parity 2e-2)."""
-        assert precision in ('fp32', 'bf16')
+        """Arithmetic of the dense layers: 'fp32' (tcgen05 3xTF32, fp32-class: reference parity 1e-5), 'bf16' (tcgen05
+        bf16 tiles, fp32 accumulate: parity 2e-2), 'fp32_simt' (FFMA cross-check) or 'tf32' (one TF32 pass)."""
+        assert precision in ('fp32', 'bf16', 'fp32_simt', 'tf32')
         self.precision = precision
         for m in self.modules():
             if m is not self and hasattr(m, 'precision'):

@@ -43,7 +43,7 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
 
 
-def assert_grads_close(got: dict, ref: dict, tol: float, what: str = ""):
+def assert_grads_close(got: dict, ref: dict, tol: float, what: str = "", slack: dict = None):
     """Per-tensor ||a-b||inf / ||b||inf <= tol for every gradient tensor.  Gradients that are structurally zero in
     exact arithmetic (e.g. the bias feeding an instance norm: the norm removes any constant) hold nothing but rounding
     noise on both sides, so a relative comparison is meaningless there: a tensor whose reference norm is below 1e-4 of
@@ -56,4 +56,35 @@ def assert_grads_close(got: dict, ref: dict, tol: float, what: str = ""):
             assert float(a.detach().abs().max()) < 1e-4 * scale, f"{what}{k}: expected a negligible gradient"
         else:
             e = rel_err(a, b)
-            assert e <= tol, f"{what}{k}: rel err {e:.3e} > {tol}"
+            t = tol + (min(slack.get(k, 0.0), tol) if slack else 0.0)     # slack: the reference side's own error, capped
+            assert e <= t, f"{what}{k}: rel err {e:.3e} > {t:.3e}"
+
+
+class cuda_decisions:
+    """Context manager that records, in call order, the discrete choices the CUDA path takes during one forward pass:
+    ("relu", bool [E, 2*dout]) per fused EdgeConv message stage -- the sign of P[target] + Q[source] evaluated with the
+    very fp32 addition the kernel performs, in ORIGINAL edge order -- and ("pool", long [n_coarse, C]) per max-pool.
+    Feed `.choices` to oracle.Decisions.replay (see its docstring for why)."""
+
+    def __enter__(self):
+        from stinet_b200 import ops
+        self.ops, self.choices = ops, []
+        self._em, self._pm = ops.edge_message, ops.pool_max
+
+        def edge_message(pq, csr):
+            h = pq.shape[1] // 2
+            with torch.no_grad():
+                m = (pq[csr._dst, :h] + pq[csr._src, h:]) > 0
+            self.choices.append(("relu", m.cpu()))
+            return self._em(pq, csr)
+
+        def pool_max(x, cl):
+            out, arg = self._pm(x, cl)
+            self.choices.append(("pool", arg.detach().long().cpu()))
+            return out, arg
+
+        ops.edge_message, ops.pool_max = edge_message, pool_max
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.edge_message, self.ops.pool_max = self._em, self._pm

@@ -41,8 +41,17 @@ def test_model_matches_reference_golden(name):
     if "ragged" in name:
         return                       # forward honours the linspace quirk; backward of ragged batches is a documented gap
     loss.backward()
-    assert rel_err(batch.x.grad, fix["grad_x"]) <= TOL
-    assert_grads_close({k: p.grad for k, p in net.named_parameters()}, fix["grads"], TOL)
+    # The golden gradients are themselves an fp32 evaluation (the reference's CPU path): |cuda - golden| is bounded by
+    # the sum of both sides' rounding errors, so each gradient tensor gets 1e-5 plus the golden's own distance from the
+    # fp64 oracle on the same input (a few 1e-6 on these small meshes).
+    orc = O.OracleSTINet(**{("norm_type" if k == "norm" else k): v for k, v in fix["kwargs"].items()})
+    orc.load_state_dict(fix["state_dict"])
+    _, _, t_grads, _ = _oracle_run(orc, fix["batch"], torch.float64)
+    golden = dict(fix["grads"], __x__=fix["grad_x"])
+    slack = {k: rel_err(golden[k], t_grads[k]) for k in golden}
+    got = {k: p.grad for k, p in net.named_parameters()}
+    got["__x__"] = batch.x.grad
+    assert_grads_close(got, golden, TOL, slack=slack)
 
 
 CASES = [
@@ -54,27 +63,41 @@ CASES = [
 ]
 
 
-def _oracle_run(orc, batch, dtype):
+def _oracle_run(orc, batch, dtype, choices=None):
     ob = copy.copy(batch)
     for k in ("x", "color"):
         ob[k] = batch[k].to(dtype)
     ob.x = ob.x.clone().requires_grad_(True)
     orc = copy.deepcopy(orc).to(dtype)
-    out = orc(ob)
+    dec = None
+    if choices is None:
+        out = orc(ob)
+    else:
+        with O.Decisions.replay(choices) as dec:
+            out = orc(ob)
     loss = O.masked_l1_loss(out, ob)
     loss.backward()
     grads = {k: p.grad for k, p in orc.named_parameters()}
     grads["__x__"] = ob.x.grad
-    return out.detach(), loss.detach(), grads
+    return out.detach(), loss.detach(), grads, dec
+
+
+# A discrete choice (ReLU sign, max-pool winner) of the fp32 CUDA path may differ from the fp64 oracle's own choice
+# only where the deciding quantity lies this close (relative to the layer's largest value) to the discontinuity,
+# i.e. within the forward tolerance.
+DECISION_MARGIN = 2e-5
 
 
 @pytest.mark.parametrize("kind,gen_kw,bsz,net_kw", CASES)
 def test_model_matches_oracle_on_seeded_meshes(kind, gen_kw, bsz, net_kw):
     """Meshes with ~1e6 ReLU decisions per layer: some pre-activation always lies within fp32 rounding of 0, where the
-    derivative is discontinuous and ANY two fp32 evaluation orders (the reference's CPU and GPU paths included) disagree
-    on isolated gradient entries (scripts/diag_flip.py shows the fp32 CPU oracle flipping against fp64 while the CUDA
-    path does not).  Protocol: the fp64 oracle is the truth; outputs must be within 1e-5 of it; every gradient tensor
-    must be within max(1e-5, 3 x the fp32 CPU oracle's own error against the same truth)."""
+    derivative is discontinuous and ANY two evaluation orders (the reference's CPU and GPU paths included) disagree on
+    isolated gradient entries.  Protocol (oracle.Decisions): the fp64 oracle replays the discrete choices the CUDA
+    forward took, which makes it a smooth function of the same inputs; against that truth outputs, loss and EVERY
+    gradient tensor must agree within 1e-5, strictly.  The choices themselves are checked for legitimacy: wherever
+    they differ from the fp64 oracle's free-running choices, the pre-activation (or the gap between the two pool
+    candidates) must be within DECISION_MARGIN of the discontinuity."""
+    from conftest import cuda_decisions
     from stinet_b200 import synthetic
     from stinet_b200.models import surfacetextureinpaintingnet as S
     torch.manual_seed(49)
@@ -83,31 +106,24 @@ def test_model_matches_oracle_on_seeded_meshes(kind, gen_kw, bsz, net_kw):
     orc = O.OracleSTINet(**{("norm_type" if k == "norm" else k): v for k, v in kw.items()})
     orc.load_state_dict(net.state_dict())
     batch = synthetic.make_batch(kind, bsz, net_kw["n_levels"], seed=49, **gen_kw)
-    t_out, t_loss, t_grads = _oracle_run(orc, batch, torch.float64)
-    c_out, c_loss, c_grads = _oracle_run(orc, batch, torch.float32)
     net = net.to(DEV)
     gb = batch.to(DEV)
     gb.x = gb.x.clone().requires_grad_(True)
-    out = net(gb)
+    with cuda_decisions() as cd:
+        out = net(gb)
     loss = _loss(out, gb)
     loss.backward()
     gb._stinet_cache.check_status()
+    t_out, t_loss, t_grads, dec = _oracle_run(orc, batch, torch.float64, cd.choices)
+    assert dec.pos == len(cd.choices)
+    print(f"choices differing from the free-running fp64 oracle: relu {dec.n_relu_diff} (margin {dec.max_relu_margin:.1e}), "
+          f"pool {dec.n_pool_diff} (margin {dec.max_pool_margin:.1e})")
+    assert dec.max_relu_margin <= DECISION_MARGIN and dec.max_pool_margin <= DECISION_MARGIN
     assert rel_err(out, t_out) <= TOL
     assert rel_err(loss, t_loss) <= TOL
     g_grads = {k: p.grad for k, p in net.named_parameters()}
     g_grads["__x__"] = gb.x.grad
-    scale = max(float(v.abs().max()) for v in t_grads.values())
-    worst = 0.0
-    for k, t in t_grads.items():
-        if float(t.abs().max()) < 1e-4 * scale:       # structurally zero gradient: rounding noise on every side
-            assert float(g_grads[k].abs().max()) < 1e-4 * scale, k
-            continue
-        denom = float(t.abs().max())
-        e_gpu = float((g_grads[k].detach().cpu().double() - t).abs().max()) / denom
-        e_cpu = float((c_grads[k].double() - t).abs().max()) / denom
-        worst = max(worst, e_gpu)
-        assert e_gpu <= max(TOL, 3 * e_cpu), f"{k}: cuda {e_gpu:.2e} vs fp32-oracle {e_cpu:.2e} (against the fp64 oracle)"
-    print(f"worst gradient error vs fp64 truth: {worst:.2e}")
+    assert_grads_close(g_grads, t_grads, TOL)
 
 
 def test_eval_no_grad_single_scene_matches_oracle():

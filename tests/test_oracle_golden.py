@@ -48,3 +48,30 @@ def test_scatter_max_first_wins_and_empty():
     out, arg = O.scatter_max(src, idx, 4)
     assert out.tolist() == [[0., 0.], [0., 0.], [3., 5.], [0., 0.]]
     assert arg.tolist() == [[3, 3], [4, 4], [1, 0], [4, 4]]
+
+
+def test_decisions_record_then_replay_reproduces_the_oracle():
+    """oracle.Decisions: replaying the oracle's own recorded choices gives the free-running result bit for bit, and
+    replaying them in fp64 stays within fp32 rounding of it (no choice is flagged beyond rounding distance)."""
+    import copy
+    from stinet_b200 import synthetic
+    torch.manual_seed(3)
+    orc = O.OracleSTINet(input_nc=10, output_nc=3, filter_type="edgeconvtransinv", ngf=8, norm_type="instance",
+                         n_blocks=2, n_levels=2, pooling_type="max")
+    batch = synthetic.make_batch("icosphere", 2, 2, seed=5, subdiv=2, mask_radius=2)
+    free = orc(batch)
+    with O.Decisions.record() as rec:
+        again = orc(batch)
+    assert torch.equal(free, again)
+    kinds = [k for k, _ in rec.recorded]
+    assert kinds.count("pool") == 2 and kinds.count("relu") == 1 + 2 + 2 + 2 + 1
+    with O.Decisions.replay(rec.recorded) as rep:
+        replayed = orc(batch)
+    assert torch.equal(free, replayed) and rep.n_relu_diff == 0 and rep.n_pool_diff == 0
+    orc64 = copy.deepcopy(orc).double()
+    b64 = copy.copy(batch)
+    b64.x = batch.x.double()
+    with O.Decisions.replay(rec.recorded) as rep64:
+        out64 = orc64(b64)
+    assert float((out64 - free.double()).abs().max()) < 1e-5
+    assert rep64.max_relu_margin <= 2e-5 and rep64.max_pool_margin <= 2e-5
