@@ -1,7 +1,8 @@
 // Segmented aggregation over CSR rows and the fused EdgeConv message stage.
-// One warp owns one CSR row and strides over the channel dimension in float4 (or scalar) columns; a row's entries
-// are accumulated sequentially in CSR order (= original edge order), so results are deterministic and follow the
-// summation order of torch_scatter's CPU kernels.  No atomics anywhere.
+// One warp owns one (CSR row, 128-channel chunk) pair -- 32 lanes x float4 -- so wide rows at the coarse levels (few
+// vertices, up to 2048 channels) still spread over the whole machine; a row's entries are accumulated sequentially in
+// CSR order (= original edge order), so results are deterministic and follow the summation order of torch_scatter's
+// CPU kernels.  No atomics anywhere.  (Scalar fallback for unaligned / odd widths: one warp per row.)
 #include "common.cuh"
 
 namespace stinet {
@@ -26,12 +27,15 @@ aggregate_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int32_t* __
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+  const int c4n = VEC ? (channels >> 2) : 0;
+  const int nchunk = VEC ? ((c4n + 31) >> 5) : 1;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t i = it / nchunk;
+    const int chunk = (int)(it - i * nchunk);
     const int beg = rowptr[i], end = rowptr[i + 1];
     const float den = (REDUCE == STINET_REDUCE_MEAN) ? (float)max(end - beg, 1) : 1.f;
     if (VEC) {
-      const int c4n = channels >> 2;
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
+      for (int c4 = chunk * 32 + lane; c4 < c4n; c4 += c4n) {   // exactly one float4 column per lane
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = beg;
         for (; k + 4 <= end; k += 4) {
@@ -79,11 +83,14 @@ aggregate_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int32_t* __
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t j = warp0; j < n_rows; j += nwarps) {
+  const int c4n = VEC ? (channels >> 2) : 0;
+  const int nchunk = VEC ? ((c4n + 31) >> 5) : 1;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t j = it / nchunk;
+    const int chunk = (int)(it - j * nchunk);
     const int beg = rowptr_s[j], end = rowptr_s[j + 1];
     if (VEC) {
-      const int c4n = channels >> 2;
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
+      for (int c4 = chunk * 32 + lane; c4 < c4n; c4 += c4n) {   // exactly one float4 column per lane
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = beg; k < end; ++k) {
           const int i = col_s[k];
@@ -121,12 +128,15 @@ edge_message_fwd_kernel(const float* __restrict__ P, int64_t ldp, const float* _
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+  const int c4n = VEC ? (hidden >> 2) : 0;
+  const int nchunk = VEC ? ((c4n + 31) >> 5) : 1;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t i = it / nchunk;
+    const int chunk = (int)(it - i * nchunk);
     const int beg = rowptr[i], end = rowptr[i + 1];
     const float den = (float)max(end - beg, 1);
     if (VEC) {
-      const int c4n = hidden >> 2;
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
+      for (int c4 = chunk * 32 + lane; c4 < c4n; c4 += c4n) {   // exactly one float4 column per lane
         const float4 p = reinterpret_cast<const float4*>(P + i * ldp)[c4];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = beg;
@@ -168,12 +178,15 @@ edge_message_bwd_target_kernel(const float* __restrict__ P, int64_t ldp, const f
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t i = warp0; i < n_rows; i += nwarps) {
+  const int c4n = VEC ? (hidden >> 2) : 0;
+  const int nchunk = VEC ? ((c4n + 31) >> 5) : 1;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t i = it / nchunk;
+    const int chunk = (int)(it - i * nchunk);
     const int beg = rowptr[i], end = rowptr[i + 1];
     const float den = (float)max(end - beg, 1);
     if (VEC) {
-      const int c4n = hidden >> 2;
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
+      for (int c4 = chunk * 32 + lane; c4 < c4n; c4 += c4n) {   // exactly one float4 column per lane
         const float4 p = reinterpret_cast<const float4*>(P + i * ldp)[c4];
         const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + i * ldd)[c4], den);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -208,11 +221,14 @@ edge_message_bwd_source_kernel(const float* __restrict__ P, int64_t ldp, const f
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t j = warp0; j < n_rows; j += nwarps) {
+  const int c4n = VEC ? (hidden >> 2) : 0;
+  const int nchunk = VEC ? ((c4n + 31) >> 5) : 1;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t j = it / nchunk;
+    const int chunk = (int)(it - j * nchunk);
     const int beg = rowptr_s[j], end = rowptr_s[j + 1];
     if (VEC) {
-      const int c4n = hidden >> 2;
-      for (int c4 = lane; c4 < c4n; c4 += 32) {
+      for (int c4 = chunk * 32 + lane; c4 < c4n; c4 += c4n) {   // exactly one float4 column per lane
         const float4 q = reinterpret_cast<const float4*>(Q + j * ldq)[c4];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int k = beg; k < end; ++k) {
@@ -251,7 +267,11 @@ inline bool vec_ok(int64_t channels, std::initializer_list<const void*> ptrs, st
   return true;
 }
 
-inline int row_grid(int64_t n_rows) { return wave_grid(n_rows, kWarpsPerCta, 8, 16); }
+// warps needed: one per (row, 128-channel chunk) on the vector path, one per row otherwise
+inline int row_grid(int64_t n_rows, int64_t channels, bool vec) {
+  const int64_t nchunk = vec ? ceil_div(channels >> 2, 32) : 1;
+  return wave_grid(n_rows * nchunk, kWarpsPerCta, 8, 16);
+}
 
 }  // namespace stinet
 
@@ -265,9 +285,9 @@ extern "C" int stinet_aggregate_fwd(const float* x, int64_t ldx, const int32_t* 
   STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldx >= channels && ldo >= channels, STINET_ERR_ARG,
                  "aggregate_fwd: bad shape");
   if (n_rows == 0) return STINET_OK;
-  const int g = row_grid(n_rows);
   const int ch = (int)channels;
   const bool v = vec_ok(channels, {x, out}, {ldx, ldo});
+  const int g = row_grid(n_rows, channels, v && reduce != STINET_REDUCE_MAX);
   switch (reduce) {
     case STINET_REDUCE_ADD:
       if (v) K(aggregate_fwd_kernel<STINET_REDUCE_ADD, true><<<g, kAggThreads, 0, s>>>(x, ldx, rowptr, col, eid, n_rows, (int32_t)n_items, ch, out, ldo, arg));
@@ -296,9 +316,9 @@ extern "C" int stinet_aggregate_bwd(const float* g_, int64_t ldg, const int32_t*
   STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldg >= channels && lddx >= channels, STINET_ERR_ARG,
                  "aggregate_bwd: bad shape");
   if (n_rows == 0) return STINET_OK;
-  const int g = row_grid(n_rows);
   const int ch = (int)channels;
   const bool v = vec_ok(channels, {g_, dx}, {ldg, lddx});
+  const int g = row_grid(n_rows, channels, v && reduce != STINET_REDUCE_MAX);
   switch (reduce) {
     case STINET_REDUCE_ADD:
       if (v) K(aggregate_bwd_kernel<STINET_REDUCE_ADD, true><<<g, kAggThreads, 0, s>>>(g_, ldg, rowptr_s, col_s, eid_s, rowptr_t, arg, n_rows, ch, dx, lddx));
@@ -327,8 +347,9 @@ extern "C" int stinet_edge_message_fwd(const float* P, int64_t ldp, const float*
   STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden && ldh >= hidden, STINET_ERR_ARG,
                  "edge_message_fwd: bad shape");
   if (n_rows == 0) return STINET_OK;
-  const int g = row_grid(n_rows);
-  if (vec_ok(hidden, {P, Q, hid}, {ldp, ldq, ldh}))
+  const bool v = vec_ok(hidden, {P, Q, hid}, {ldp, ldq, ldh});
+  const int g = row_grid(n_rows, hidden, v);
+  if (v)
     K(edge_message_fwd_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, rowptr_t, col_t, n_rows, (int)hidden, hid, ldh));
   else
     K(edge_message_fwd_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, rowptr_t, col_t, n_rows, (int)hidden, hid, ldh));
@@ -344,8 +365,9 @@ extern "C" int stinet_edge_message_bwd_target(const float* P, int64_t ldp, const
   STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden && ldd >= hidden && lddp >= hidden,
                  STINET_ERR_ARG, "edge_message_bwd_target: bad shape");
   if (n_rows == 0) return STINET_OK;
-  const int g = row_grid(n_rows);
-  if (vec_ok(hidden, {P, Q, dhid, dP}, {ldp, ldq, ldd, lddp}))
+  const bool v = vec_ok(hidden, {P, Q, dhid, dP}, {ldp, ldq, ldd, lddp});
+  const int g = row_grid(n_rows, hidden, v);
+  if (v)
     K(edge_message_bwd_target_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, col_t, n_rows, (int)hidden, dP, lddp));
   else
     K(edge_message_bwd_target_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, col_t, n_rows, (int)hidden, dP, lddp));
@@ -361,8 +383,9 @@ extern "C" int stinet_edge_message_bwd_source(const float* P, int64_t ldp, const
   STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden && ldd >= hidden && lddq >= hidden,
                  STINET_ERR_ARG, "edge_message_bwd_source: bad shape");
   if (n_rows == 0) return STINET_OK;
-  const int g = row_grid(n_rows);
-  if (vec_ok(hidden, {P, Q, dhid, dQ}, {ldp, ldq, ldd, lddq}))
+  const bool v = vec_ok(hidden, {P, Q, dhid, dQ}, {ldp, ldq, ldd, lddq});
+  const int g = row_grid(n_rows, hidden, v);
+  if (v)
     K(edge_message_bwd_source_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, rowptr_s, col_s, n_rows, (int)hidden, dQ, lddq));
   else
     K(edge_message_bwd_source_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, dhid, ldd, rowptr_t, rowptr_s, col_s, n_rows, (int)hidden, dQ, lddq));

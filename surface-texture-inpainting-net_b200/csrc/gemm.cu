@@ -166,13 +166,18 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmArgs g) {
   }
 }
 
+// fixed-order sum of the split partials (+ bias on rows with rowmask > 0): deterministic second stage of a split GEMM
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t IJ, int J,
-                                     float* __restrict__ out, int64_t ldo) {
+                                     float* __restrict__ out, int64_t ldo, const float* __restrict__ bias,
+                                     const int32_t* __restrict__ rowmask) {
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < IJ;
        idx += (int64_t)gridDim.x * blockDim.x) {
     float t = 0.f;
     for (int s = 0; s < splits; ++s) t += part[(int64_t)s * IJ + idx];
-    out[(idx / J) * ldo + (idx % J)] = t;
+    const int64_t i = idx / J;
+    const int j = (int)(idx - i * J);
+    if (bias != nullptr && (rowmask == nullptr || rowmask[i] > 0)) t += bias[j];
+    out[i * ldo + j] = t;
   }
 }
 
@@ -264,20 +269,29 @@ static int pick_splits(int64_t I, int64_t J, int64_t T) {
   return (int)(s < 1 ? 1 : s);
 }
 
-// split of the reduction dimension for the tensor-core wgrad: about two CTAs per SM, at least 256 rows per split,
-// whole 64-row k-blocks per split
+// Split of the reduction dimension for the persistent tensor-core kernel (one CTA per SM walks the work units).
+// Enough output tiles to fill the SMs: no split.  Otherwise pick the split count S that minimises the number of
+// unit rounds per unit of work, ceil(tiles*S / 148) / S, with at least 256 reduction elements per split and whole
+// 64-element k-blocks.  wgrad (few tiles, very long reduction) may use many splits, fwd / dgrad at most 8.
 struct TcSplit { int splits; int64_t t_per; };
-static TcSplit tc_split(int64_t I, int64_t J, int64_t T) {
+static TcSplit tc_split(int64_t I, int64_t J, int64_t T, int max_splits) {
   const int64_t bn = J <= 64 ? 64 : 128;
   const int64_t tiles = ceil_div(I, 128) * ceil_div(J, bn);
-  int64_t want = ceil_div(2 * kSMs, tiles);
-  const int64_t cap = ceil_div(T, 256);
-  if (want > cap) want = cap;
-  if (want < 1) want = 1;
-  int64_t t_per = ceil_div(ceil_div(T, want), 64) * 64;
+  int64_t best = 1;
+  if (tiles < (kSMs * 7) / 8) {
+    int64_t cap = T / 256;
+    if (cap > max_splits) cap = max_splits;
+    double best_cost = (double)ceil_div(tiles, kSMs);
+    for (int64_t sp = 2; sp <= cap; ++sp) {
+      const double cost = (double)ceil_div(tiles * sp, kSMs) / (double)sp;
+      if (cost < best_cost * 0.97) { best_cost = cost; best = sp; }
+    }
+  }
+  int64_t t_per = ceil_div(ceil_div(T, best), 64) * 64;
   if (t_per < 64) t_per = 64;
   return TcSplit{(int)ceil_div(T, t_per), t_per};
 }
+constexpr int kWgradMaxSplits = 2 * kSMs, kFwdMaxSplits = 8;
 
 static int tc_mode(int precision) {
   switch (precision) {
@@ -299,9 +313,13 @@ static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K, int precis
   GemmWs w;
   const int64_t rows = M > 0 ? M : 1;
   int splits = pick_splits(N, K, rows);
-  const int tcs = tc_split(N, K, rows).splits;
+  const int tcs = tc_split(N, K, rows, kWgradMaxSplits).splits;
   if (tcs > splits) splits = tcs;
-  const size_t sk = up(sizeof(float) * (size_t)splits * N * K);
+  size_t sk_elems = (size_t)splits * N * K;                                                   // wgrad partials
+  const int sf = tc_split(rows, N, K, kFwdMaxSplits).splits, sd = tc_split(rows, K, N, kFwdMaxSplits).splits;
+  if (sf > 1 && (size_t)sf * rows * N > sk_elems) sk_elems = (size_t)sf * rows * N;          // fwd partials
+  if (sd > 1 && (size_t)sd * rows * K > sk_elems) sk_elems = (size_t)sd * rows * K;          // dgrad partials
+  const size_t sk = up(sizeof(float) * sk_elems);
   const size_t cs = up(sizeof(float) * (size_t)ceil_div(rows, kColsumRows) * N);
   const bool b16 = precision == STINET_PREC_BF16;
   const size_t a16 = b16 ? up(2 * (size_t)rows * K) : 0, w16 = b16 ? up(2 * (size_t)N * K) : 0,
@@ -354,7 +372,22 @@ extern "C" int stinet_linear_fwd(const float* A, int64_t lda, const float* W, in
         p.A = w.a16; p.lda = K; p.B = w.w16; p.ldb = K;
       }
     }
-    if (ok && tc::eligible(p)) return tc::run(p, s);
+    if (ok && tc::eligible(p)) {
+      const TcSplit sp = tc_split(M, N, K, kFwdMaxSplits);
+      if (sp.splits > 1) {
+        GemmWs w = carve_gemm(workspace, M, N, K, precision);
+        if (workspace && workspace_bytes >= w.bytes) {     // without a workspace the unsplit kernel is still correct
+          p.C = w.splitk; p.ldc = N; p.bias = nullptr; p.rowmask = nullptr;
+          p.splits = sp.splits; p.t_per_split = sp.t_per;
+          int rc = tc::run(p, s);
+          if (rc) return rc;
+          K(splitk_reduce_kernel<<<wave_grid(M * N, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, M * N, (int)N, C, ldc,
+                                                                        bias, rowmask));
+          return check_launch("linear_fwd");
+        }
+      }
+      return tc::run(p, s);
+    }
   }
   GemmArgs g{A, lda, W, ldw, C, ldc, bias, rowmask, (int)M, (int)N, (int)K, (int)K};
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
@@ -386,7 +419,21 @@ extern "C" int stinet_linear_dgrad(const float* dC, int64_t ldc, const float* W,
         p.A = w.c16; p.lda = N; p.B = w.w16; p.ldb = K;
       }
     }
-    if (ok && tc::eligible(p)) return tc::run(p, s);
+    if (ok && tc::eligible(p)) {
+      const TcSplit sp = tc_split(M, K, N, kFwdMaxSplits);
+      if (sp.splits > 1) {
+        GemmWs w = carve_gemm(workspace, M, N, K, precision);
+        if (workspace && workspace_bytes >= w.bytes) {
+          p.C = w.splitk; p.ldc = K; p.splits = sp.splits; p.t_per_split = sp.t_per;
+          int rc = tc::run(p, s);
+          if (rc) return rc;
+          K(splitk_reduce_kernel<<<wave_grid(M * K, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, M * K, (int)K, dA, lda,
+                                                                        nullptr, nullptr));
+          return check_launch("linear_dgrad");
+        }
+      }
+      return tc::run(p, s);
+    }
   }
   GemmArgs g{dC, ldc, W, ldw, dA, lda, nullptr, nullptr, (int)M, (int)K, (int)N, (int)N};
   dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(M, BM), 1);
@@ -408,7 +455,7 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
   bool done = false;
   const int mode = tc_mode(precision);
   if (mode >= 0 && M > 0) {
-    const TcSplit sp = tc_split(N, K, M);
+    const TcSplit sp = tc_split(N, K, M, kWgradMaxSplits);
     tc::Problem p{dC, ldc, true, A, lda, true, sp.splits == 1 ? dW : w.splitk, sp.splits == 1 ? ldw : K,
                   nullptr, nullptr, N, K, M, sp.splits, sp.t_per, mode};
     bool ok = true;
@@ -424,7 +471,8 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
       int rc = tc::run(p, s);
       if (rc) return rc;
       if (sp.splits > 1)
-        K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, N * K, (int)K, dW, ldw));
+        K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, N * K, (int)K, dW, ldw, nullptr,
+                                                                        nullptr));
       done = true;
     }
   }
@@ -438,7 +486,8 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
     } else {
       GemmArgs g{dC, ldc, A, lda, w.splitk, K, nullptr, nullptr, (int)N, (int)K, (int)M, t_per};
       K(gemm_kernel<false, false><<<grid, kGemmThreads, 0, s>>>(g));
-      K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, splits, N * K, (int)K, dW, ldw));
+      K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, splits, N * K, (int)K, dW, ldw, nullptr,
+                                                                      nullptr));
     }
   }
   if (dbias) {

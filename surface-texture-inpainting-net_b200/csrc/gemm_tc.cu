@@ -50,6 +50,23 @@ struct TcArgs {
   int split_acc;                   // fp32 mode: keep the hi*lo + lo*hi correction terms in their own TMEM accumulator
 };
 
+#ifdef STINET_TC_DEBUG
+// cycles CTA 0 spends waiting at each barrier family (build with -DSTINET_TC_DEBUG; read with stinet_tc_debug_read):
+// 0 producer<-empty, 1 split<-full, 2 mma<-operands, 3 mma<-tmem_empty, 4 epilogue<-tmem_full, 5 epilogue store
+// phase, 6 total kernel cycles, 7 split work, 8 units processed by CTA 0
+__device__ unsigned long long g_tc_dbg[16];
+#define DBG_T0() const long long dbg_t0 = clock64()
+#define DBG_ADD(slot) dbg_acc[slot] += clock64() - dbg_t0
+#define DBG_DECL() long long dbg_acc[16] = {0}
+#define DBG_FLUSH(cond, lo, hi) \
+  if ((cond) && blockIdx.x == 0) { for (int d_ = lo; d_ <= hi; ++d_) g_tc_dbg[d_] = (unsigned long long)dbg_acc[d_]; }
+#else
+#define DBG_T0()
+#define DBG_ADD(slot)
+#define DBG_DECL()
+#define DBG_FLUSH(cond, lo, hi)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // PTX helpers
 
@@ -253,10 +270,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       int s = 0;
       uint32_t ph = 0;
+      DBG_DECL();
       for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
         const Unit w = decode(u);
         for (int kb = 0; kb < w.nkb; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
+          { DBG_T0(); mbar_wait(empty_bar(s), ph ^ 1u); DBG_ADD(0); }
           mbar_expect_tx(full_bar(s), C_::kLoadBytes);
           const int t0 = w.t_begin + kb * C_::BKE;
           const uint32_t a_dst = base + s * C_::kStageBytes;
@@ -278,6 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
+      DBG_FLUSH(true, 0, 0);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -294,17 +313,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       uint32_t acc_it = 0;
+      DBG_DECL();
+#ifdef STINET_TC_DEBUG
+      const long long dbg_start = clock64();
+#endif
       for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
         const Unit w = decode(u);
+#ifdef STINET_TC_DEBUG
+        dbg_acc[8] += 1;
+#endif
         for (int kb0 = 0; kb0 < w.nkb; kb0 += g.promote) {
           const int kb1 = min(w.nkb, kb0 + g.promote);
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-          mbar_wait(tempty_bar(buf), aph ^ 1u);   // the epilogue has drained this accumulator buffer
+          { DBG_T0(); mbar_wait(tempty_bar(buf), aph ^ 1u); DBG_ADD(3); }  // the epilogue has drained this accumulator buffer
           tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
           const uint32_t tmem_s = g.split_acc ? tmem_d + 2 * BN : tmem_d;   // correction-term accumulator
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(C_::kSplit ? conv_bar(s) : full_bar(s), ph);
+            { DBG_T0(); mbar_wait(C_::kSplit ? conv_bar(s) : full_bar(s), ph); DBG_ADD(2); }
             tcgen05_fence_after();
             const uint32_t a_hi = base + s * C_::kStageBytes;
             const uint32_t b_hi = a_hi + C_::kABytes;
@@ -337,6 +363,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ++acc_it;
         }
       }
+#ifdef STINET_TC_DEBUG
+      dbg_acc[6] = clock64() - dbg_start;
+#endif
+      DBG_FLUSH(true, 2, 3);
+      DBG_FLUSH(true, 6, 6);
+      DBG_FLUSH(true, 8, 8);
     }
   } else if (warp < kEpiWarp0) {
     // ===== operand split (fp32 mode): x = hi + lo, hi = x rounded to TF32 (written in place), lo = x - hi (exact in
@@ -346,10 +378,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int kChunks = C_::kLoadBytes / 16;
       int s = 0;
       uint32_t ph = 0;
+      DBG_DECL();
       for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
         const Unit w = decode(u);
         for (int kb = 0; kb < w.nkb; ++kb) {
-          mbar_wait(full_bar(s), ph);
+          { DBG_T0(); mbar_wait(full_bar(s), ph); DBG_ADD(1); }
+          DBG_T0();
           uint4* hi = reinterpret_cast<uint4*>(base_ptr + (size_t)s * C_::kStageBytes);
           uint4* lo = hi + kChunks;
 #pragma unroll 4
@@ -365,9 +399,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
           mbar_arrive(conv_bar(s));
+          DBG_ADD(7);
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
+      DBG_FLUSH(threadIdx.x == 64, 1, 1);
+      DBG_FLUSH(threadIdx.x == 64, 7, 7);
     }
   } else {
     // ===== epilogue: TMEM -> registers (RN accumulation across promotion chunks) -> swizzled smem transpose ->
@@ -379,11 +416,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4* stage = reinterpret_cast<float4*>(base_ptr + staging_off + (size_t)ew * 4096);
     float acc[EC];
     uint32_t acc_it = 0;
+    DBG_DECL();
     for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
       const Unit w = decode(u);
       for (int kb0 = 0; kb0 < w.nkb; kb0 += g.promote) {
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-        mbar_wait(tfull_bar(buf), aph);
+        { DBG_T0(); mbar_wait(tfull_bar(buf), aph); DBG_ADD(4); }
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(h * EC);
 #pragma unroll
@@ -410,6 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ++acc_it;
       }
       // ---- write the tile out
+      DBG_T0();
       const int row = w.i0 + q * 32 + lane;                // the row this thread holds
       const bool add_bias = g.bias != nullptr && row < g.I && (g.rowmask == nullptr || g.rowmask[row] > 0);
       float* cbase = g.C + (int64_t)w.z * g.I * g.ldc;
@@ -437,7 +476,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
       }
+      DBG_ADD(5);
     }
+    DBG_FLUSH(threadIdx.x == 32 * kEpiWarp0, 4, 5);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -563,3 +604,9 @@ int run(const Problem& p, cudaStream_t s) {
 
 }  // namespace tc
 }  // namespace stinet
+
+#ifdef STINET_TC_DEBUG
+extern "C" int stinet_tc_debug_read(unsigned long long* out16) {
+  return cudaMemcpyFromSymbol(out16, stinet::tc::g_tc_dbg, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -3;
+}
+#endif

@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstinet_b200.so")
+LIB_PATH = os.environ.get("STINET_B200_LIB") or os.path.join(_HERE, "libstinet_b200.so")   # override: debug builds only
 
 P, I64, I, F, SZ = c_void_p, c_int64, c_int, c_float, c_size_t
 

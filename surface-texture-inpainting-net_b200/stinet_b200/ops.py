@@ -88,7 +88,20 @@ class LinearFn(Function):
 
 
 def linear(x, weight, bias=None, rowmask=None, precision="fp32"):
-    return LinearFn.apply(x, weight, bias, rowmask, precision)
+    """y = x W^T + b.  TMA (the tensor-core path) needs 16-byte row pitches, so a reduction width or an output width
+    that is not a multiple of 4 floats (the 10-channel input, the 3-channel head) is zero-padded: the extra products
+    are exact zeros and the extra output columns are sliced away again."""
+    k, n = x.shape[1], weight.shape[0]
+    pk, pn = (-k) % 4, (-n) % 4
+    if not (pk or pn):
+        return LinearFn.apply(x, weight, bias, rowmask, precision)
+    if pk:
+        x = torch.nn.functional.pad(x, (0, pk))
+    weight = torch.nn.functional.pad(weight, (0, pk, 0, pn))
+    if bias is not None and pn:
+        bias = torch.nn.functional.pad(bias, (0, pn))
+    y = LinearFn.apply(x, weight, bias, rowmask, precision)
+    return y[:, :n] if pn else y
 
 
 # ------------------------------------------------------------------------------------------------------------
