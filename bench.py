@@ -46,6 +46,16 @@ WORKLOADS = {
                  net=dict(input_nc=4, output_nc=3, ngf=64, filter_type="edgeconv", norm="instance", n_blocks=9,
                           n_levels=4, pooling_type="max"),
                  name="STINet 2D, 4 x 128x128 image-grid graphs, 4 pool levels"),
+    # configs[2]: ScanNet-scale scene, full-scene inference (eval / no_grad, batch=None norms)
+    "cfg3": dict(kind="plane", gen=dict(rows=500, cols=500, mask_cover=0.05), batch=1, mode="infer",
+                 net=dict(input_nc=10, output_nc=3, ngf=64, filter_type="edgeconvtransinv", norm="instance", n_blocks=9,
+                          n_levels=4, pooling_type="max"),
+                 name="STINet 3D full-scene inference, synthetic 250,000-vertex plane mesh (1.5 M edges), 4 trace-map levels"),
+    # configs[4]: one ~2 M-vertex scene per GPU, 5 trace-map levels (run with --dtype bf16)
+    "cfg5": dict(kind="plane", gen=dict(rows=1448, cols=1448, mask_cover=0.0001, mask_radius=8), batch=1,
+                 net=dict(input_nc=10, output_nc=3, ngf=64, filter_type="edgeconvtransinv", norm="instance", n_blocks=9,
+                          n_levels=5, pooling_type="max"),
+                 name="STINet 3D, one synthetic 2,096,704-vertex plane mesh (12.6 M edges) per GPU, 5 trace-map levels"),
     "tiny": dict(kind="icosphere", gen=dict(subdiv=3, mask_radius=3), batch=2,
                  net=dict(input_nc=10, output_nc=3, ngf=16, filter_type="edgeconvtransinv", norm="instance", n_blocks=2,
                           n_levels=2, pooling_type="max"),
@@ -139,7 +149,13 @@ def run_reference(args, wl, rank, world):
     n0 = b.x.shape[0]
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
 
+    infer = wl.get("mode") == "infer"
+
     def step():
+        if infer:
+            with torch.no_grad():
+                net(b)
+            return
         net.zero_grad(set_to_none=True)
         out = net(b)
         O.masked_l1_loss(out, b).backward()
@@ -151,9 +167,10 @@ def run_reference(args, wl, rank, world):
         step()
     dt = (time.perf_counter() - t0) / steps
     v = n0 / dt
-    sample = f"1 of {wl['batch']} graphs ({n0} vertices), fwd+loss+bwd, {steps} timed steps after {warm} warm-up"
+    what = "forward (eval, no_grad)" if infer else "fwd+loss+bwd"
+    sample = f"1 of {wl['batch']} graphs ({n0} vertices), {what}, {steps} timed steps after {warm} warm-up"
     print(json.dumps({
-        "impl": "reference", "metric": "mesh vertices/sec fwd+bwd", "value": v, "unit": "vertices/s", "n_gpus": 0,
+        "impl": "reference", "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": v, "unit": "vertices/s", "n_gpus": 0,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "sample": sample},
@@ -173,7 +190,13 @@ def cpu_baseline(wl, budget_s=25.0):
     net = O.OracleSTINet(**nk)
     b = synthetic.make_batch(wl["kind"], 1, wl["net"]["n_levels"], seed=49, **wl["gen"])
 
+    infer = wl.get("mode") == "infer"
+
     def step():
+        if infer:
+            with torch.no_grad():
+                net(b)
+            return
         net.zero_grad(set_to_none=True)
         O.masked_l1_loss(net(b), b).backward()
 
@@ -186,7 +209,8 @@ def cpu_baseline(wl, budget_s=25.0):
         step()
     dt = (time.perf_counter() - t0) / n
     return {"value": b.x.shape[0] / dt, "unit": "vertices/s", "cores": cores, "kind": "port",
-            "sample": f"CPU oracle port (PyG absent), 1 of {wl['batch']} graphs ({b.x.shape[0]} vertices), fwd+loss+bwd, "
+            "sample": f"CPU oracle port (PyG absent), 1 of {wl['batch']} graphs ({b.x.shape[0]} vertices), "
+                      f"{'forward (eval, no_grad)' if infer else 'fwd+loss+bwd'}, "
                       f"{n} timed steps after 1 warm-up, fp32, recompute off"}
 
 
@@ -197,12 +221,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="stinet", choices=["stinet", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16", "bf16_1pass", "tf32"],
+                    help="arithmetic of the dense layers: fp32 = 3xTF32 tcgen05 (1e-5 parity); bf16 = bf16 tcgen05 tiles on "
+                         "hi/lo-split operands (whole network within 2e-2); bf16_1pass = one bf16 pass (2e-2 per operator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch every kernel from Python instead of replaying the captured whole-step CUDA graph")
+    ap.add_argument("--kernels-out", default=None, help="write the full per-entry-point CUDA-event table (JSON) here")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket timed region 1 with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -225,7 +252,10 @@ def main():
     W, K = max(args.warmup, 3), args.steps
 
     torch.manual_seed(49)                                    # same initial weights on every rank
-    net = S.define_G(**wl["net"], gpu_ids=[dev], precision=args.dtype).train()
+    precision = {"fp32": "fp32", "bf16": "bf16x3", "bf16_1pass": "bf16", "tf32": "tf32"}[args.dtype]
+    infer = wl.get("mode") == "infer"
+    net = S.define_G(**wl["net"], gpu_ids=[dev], precision=precision)
+    net = net.eval() if infer else net.train()
     host = synthetic.make_batch(wl["kind"], wl["batch"], wl["net"]["n_levels"], seed=49 + 1000 * rank, **wl["gen"])
     host = host.pin_memory()
     n0 = int(host.x.shape[0])
@@ -236,6 +266,10 @@ def main():
     def eager_step(b, read_loss=False):
         b = copy.copy(b)
         b.__dict__.pop("_stinet_cache", None)                # every step rebuilds the graph structure (new batch)
+        if infer:                                            # full-scene inference: structure build + forward
+            with torch.no_grad():
+                out = net(b)
+            return float(out[0, 0].item()) if read_loss else out
         reducer.zero_grad()
         loss = masked_l1(net(b), b)
         loss.backward()
@@ -244,7 +278,7 @@ def main():
         return loss.item() if read_loss else loss
 
     graphed = None
-    if args.no_graph:
+    if args.no_graph or infer:
         step = eager_step
     else:
         # the public whole-step API: the same work (structure build + fwd + loss + bwd + Adam) captured once per batch
@@ -297,7 +331,7 @@ def main():
     # ---- timed region 2: end to end through the public API from pinned host memory ----------------------------
     e2e = None
     if not args.no_e2e:
-        feed = (lambda: host.to(dev, non_blocking=True)) if args.no_graph else (lambda: host)
+        feed = (lambda: host.to(dev, non_blocking=True)) if graphed is None else (lambda: host)
         for _ in range(2):
             step(feed(), read_loss=True)
         barrier()
@@ -324,26 +358,54 @@ def main():
                        "GBps": round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1) if r["ms"] > 0 else None,
                        "TFLOPs": round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 2) if r["ms"] > 0 else None}
                    for k, r in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:12]}
-        top, r = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        if args.kernels_out:
+            with open(args.kernels_out, "w") as f:
+                json.dump({"total_ms_per_step": total / 2, "kernels": {
+                    k: {"calls_per_step": r["calls"] // 2, "ms_per_step": r["ms"] / 2, "share": r["ms"] / total,
+                        "GBps": r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else None,
+                        "TFLOPs": r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else None}
+                    for k, r in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}}, f, indent=1)
+        # dominant kernel = the kernel FAMILY (entry point, all shapes) with the largest share of device time
+        fam = {}
+        for k, r in summ.items():
+            f = fam.setdefault(k.split("[")[0], {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            for q in f:
+                f[q] += r[q]
+        top, r = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        bf16_peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         if top.startswith("linear"):
             ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
-            peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
-                        "peak_source": f"{pk_src} bf16 dense GEMM (sustained); this kernel runs the exact-fp32 FFMA path"}
+            # MMA passes per algorithmic product, and the tensor-pipe rate of the operand type relative to bf16
+            passes, rate = {"fp32": (3, 0.5), "bf16x3": (3, 1.0), "bf16": (1, 1.0), "tf32": (1, 0.5)}[precision]
+            roofline = {"kernel": f"gemm_tc_kernel ({top}, all shapes)", "bound": "tensor", "achieved": ach,
+                        "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
+                        "peak_source": f"{pk_src} dense bf16 GEMM (sustained)",
+                        "mode": f"{precision}: {passes} tcgen05 pass(es) per product at {rate}x the bf16 rate; achieved counts "
+                                f"algorithmic flops 2MNK once, so the ceiling of this mode is peak*{rate / passes:.3f}",
+                        "frac_of_mode_ceiling": ach / (bf16_peak * rate / passes)}
         else:
             ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth"}
         roofline["share_of_step"] = r["ms"] / total
         roofline["ms_per_launch"] = r["ms"] / r["calls"]
-        # the dominant HBM-bound kernel is always reported too (north_star: aggregation / pool kernels vs HBM peak)
-        hbm = {k: v for k, v in summ.items() if not k.startswith("linear") and v["ms"] > 0}
-        if hbm:
-            k2, r2 = max(hbm.items(), key=lambda kv: kv[1]["ms"])
-            roofline["top_hbm_kernel"] = {"kernel": k2, "achieved_GBps": r2["bytes"] / (r2["ms"] * 1e-3) / 1e9,
-                                          "frac": r2["bytes"] / (r2["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"],
-                                          "share_of_step": r2["ms"] / total}
+        # measured DRAM traffic per launch of the dominant kernels (ncu --set full, profiles/): largest shape of each
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            ent = tj.get(args.workload, {}).get(top)
+            if ent:
+                roofline["traffic"] = ent.get("dram_bytes_per_launch")
+                roofline["traffic_note"] = ent.get("note")
+        # the HBM-bound families are always reported too (north_star: aggregation / pool / norm kernels vs HBM peak);
+        # algorithmic bytes follow SURVEY 8d's no-cache-reuse convention, so L2 hits can push a fraction above 1
+        hbm = {k: v for k, v in fam.items() if not k.startswith("linear") and v["ms"] > 0 and v["bytes"] > 0}
+        roofline["hbm_kernels"] = {
+            k: {"achieved_GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"], 3),
+                "share_of_step": round(v["ms"] / total, 4), "launches_per_step": v["calls"] // 2}
+            for k, v in sorted(hbm.items(), key=lambda kv: -kv[1]["ms"])}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -351,13 +413,16 @@ def main():
 
     if rank == 0:
         print(json.dumps({
-            "metric": "mesh vertices/sec fwd+bwd", "value": value, "unit": "vertices/s", "n_gpus": world, "steps": K,
+            "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": value,
+            "unit": "vertices/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16_1pass": "bf16", "tf32": "tf32"}[args.dtype], "data": "synthetic",
             "config": {"workload": wl["name"], "vertices_per_step_per_gpu": n0,
-                       "step": "graph-structure (CSR) build + forward + masked L1 + backward"
+                       "step": "graph-structure (CSR) build + forward (eval, no_grad)" if infer else
+                               "graph-structure (CSR) build + forward + masked L1 + backward"
                                + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam(amsgrad) step",
-                       "launch": "python launches" if args.no_graph else "whole-step CUDA graph replay (stinet_b200.engine)",
+                       "dense_layers": precision,
+                       "launch": "python launches" if graphed is None else "whole-step CUDA graph replay (stinet_b200.engine)",
                        "l2": "per-step working set (activations + weights, several GB) is far larger than the 126 MB L2; "
                              "no explicit flush"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,

@@ -41,10 +41,13 @@ enum { STINET_REDUCE_ADD = 0, STINET_REDUCE_MEAN = 1, STINET_REDUCE_MAX = 2 };
 /* arithmetic of the dense layers (storage at the ABI is fp32, accumulation is always fp32):
  *   FP32      tcgen05 kind::tf32, every product as hi*hi + hi*lo + lo*hi of TF32-rounded halves (fp32-class error,
  *             the reference's 1e-5 bar); operands TMA cannot address (row pitch % 16 B != 0) run on FFMA tiles
- *   BF16      operands cast to bf16 in the workspace, tcgen05 kind::f16 (the 2e-2 bar of the bf16 mode)
+ *   BF16      operands cast to bf16 in the workspace, tcgen05 kind::f16 (2e-2 per operator)
+ *   BF16X3    operands split into two bf16 planes x = hi + lo in the workspace, tcgen05 kind::f16 on
+ *             hi*hi + hi*lo + lo*hi (~2^-16 per product: keeps a whole network within the 2e-2 bar)
  *   FP32_SIMT FFMA tiles only (cross-check of the tensor-core paths)
  *   TF32      one tcgen05 kind::tf32 pass (~1e-3) */
-enum { STINET_PREC_FP32 = 0, STINET_PREC_BF16 = 1, STINET_PREC_FP32_SIMT = 2, STINET_PREC_TF32 = 3 };
+enum { STINET_PREC_FP32 = 0, STINET_PREC_BF16 = 1, STINET_PREC_FP32_SIMT = 2, STINET_PREC_TF32 = 3,
+       STINET_PREC_BF16X3 = 4 };
 enum { STINET_ACT_NONE = 0, STINET_ACT_ELU = 1 };
 
 int stinet_abi_version(void);

@@ -243,8 +243,10 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
 
 // fp32 -> bf16 cast of a row-major matrix (bf16 mode: the tensor-core kernel reads bf16 operands through TMA).
 // cols % 8 == 0, 16 B aligned rows on both sides; one thread converts 8 elements.
+// With a `lo` plane (bf16x3 mode) the rounding residual x - float(hi) is stored too, so hi + lo carries 16 significand bits.
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
-                                                        __nv_bfloat16* __restrict__ y, int64_t ldy) {
+                                                        __nv_bfloat16* __restrict__ y, int64_t ldy,
+                                                        __nv_bfloat16* __restrict__ lo) {
   const int cpr = cols >> 3;
   const int64_t total = rows * cpr;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -258,6 +260,16 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
     *reinterpret_cast<uint4*>(y + r * ldy + c) = o;
+    if (lo != nullptr) {
+      const float2 h0 = __bfloat1622float2(p0), h1 = __bfloat1622float2(p1), h2 = __bfloat1622float2(p2),
+                   h3 = __bfloat1622float2(p3);
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(a.x - h0.x, a.y - h0.y), q1 = __floats2bfloat162_rn(a.z - h1.x, a.w - h1.y);
+      __nv_bfloat162 q2 = __floats2bfloat162_rn(b.x - h2.x, b.y - h2.y), q3 = __floats2bfloat162_rn(b.z - h3.x, b.w - h3.y);
+      uint4 l;
+      l.x = *reinterpret_cast<uint32_t*>(&q0); l.y = *reinterpret_cast<uint32_t*>(&q1);
+      l.z = *reinterpret_cast<uint32_t*>(&q2); l.w = *reinterpret_cast<uint32_t*>(&q3);
+      *reinterpret_cast<uint4*>(lo + r * ldy + c) = l;
+    }
   }
 }
 
@@ -298,14 +310,17 @@ static int tc_mode(int precision) {
     case STINET_PREC_FP32: return tc::MODE_TF32X3;
     case STINET_PREC_BF16: return tc::MODE_BF16;
     case STINET_PREC_TF32: return tc::MODE_TF32X1;
+    case STINET_PREC_BF16X3: return tc::MODE_BF16X3;
     default: return -1;
   }
 }
-static bool valid_precision(int p) { return p >= STINET_PREC_FP32 && p <= STINET_PREC_TF32; }
+static bool valid_precision(int p) { return p >= STINET_PREC_FP32 && p <= STINET_PREC_BF16X3; }
+static bool is_bf16_mode(int mode) { return mode == tc::MODE_BF16 || mode == tc::MODE_BF16X3; }
 
 struct GemmWs {
   float *splitk, *colsum;
-  __nv_bfloat16 *a16, *w16, *c16;
+  __nv_bfloat16 *a16, *w16, *c16;          // bf16 copies of A [M,K], W [N,K], dC [M,N]
+  __nv_bfloat16 *a16lo, *w16lo, *c16lo;    // bf16x3 mode: the residual planes (nullptr otherwise)
   size_t bytes;
 };
 static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K, int precision) {
@@ -321,23 +336,29 @@ static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K, int precis
   if (sd > 1 && (size_t)sd * rows * K > sk_elems) sk_elems = (size_t)sd * rows * K;          // dgrad partials
   const size_t sk = up(sizeof(float) * sk_elems);
   const size_t cs = up(sizeof(float) * (size_t)ceil_div(rows, kColsumRows) * N);
-  const bool b16 = precision == STINET_PREC_BF16;
-  const size_t a16 = b16 ? up(2 * (size_t)rows * K) : 0, w16 = b16 ? up(2 * (size_t)N * K) : 0,
-               c16 = b16 ? up(2 * (size_t)rows * N) : 0;
+  const bool x3 = precision == STINET_PREC_BF16X3;
+  const bool b16 = precision == STINET_PREC_BF16 || x3;
+  const size_t planes = x3 ? 2 : 1;
+  const size_t a1 = up(2 * (size_t)rows * K), w1 = up(2 * (size_t)N * K), c1 = up(2 * (size_t)rows * N);
+  const size_t a16 = b16 ? planes * a1 : 0, w16 = b16 ? planes * w1 : 0, c16 = b16 ? planes * c1 : 0;
   char* p = static_cast<char*>(base);
   w.splitk = reinterpret_cast<float*>(p);
   w.colsum = reinterpret_cast<float*>(p + sk);
   w.a16 = reinterpret_cast<__nv_bfloat16*>(p + sk + cs);
   w.w16 = reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16);
   w.c16 = reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16 + w16);
+  w.a16lo = x3 ? reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a1) : nullptr;
+  w.w16lo = x3 ? reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16 + w1) : nullptr;
+  w.c16lo = x3 ? reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16 + w16 + c1) : nullptr;
   w.bytes = sk + cs + a16 + w16 + c16;
   return w;
 }
 
 // fp32 matrix the cast kernel (and TMA) can address with 16-byte accesses
 static bool castable(const float* x, int64_t ld, int64_t cols) { return aligned16(x) && ld % 4 == 0 && cols % 8 == 0; }
-static void cast_bf16(const float* x, int64_t ld, int64_t rows, int64_t cols, __nv_bfloat16* y, cudaStream_t s) {
-  K(cast_bf16_kernel<<<wave_grid(rows * (cols / 8), 256, 8), 256, 0, s>>>(x, ld, rows, (int)cols, y, cols));
+static void cast_bf16(const float* x, int64_t ld, int64_t rows, int64_t cols, __nv_bfloat16* y, __nv_bfloat16* lo,
+                      cudaStream_t s) {
+  K(cast_bf16_kernel<<<wave_grid(rows * (cols / 8), 256, 8), 256, 0, s>>>(x, ld, rows, (int)cols, y, cols, lo));
 }
 
 }  // namespace stinet
@@ -361,15 +382,15 @@ extern "C" int stinet_linear_fwd(const float* A, int64_t lda, const float* W, in
   if (mode >= 0) {
     tc::Problem p{A, lda, false, W, ldw, false, C, ldc, bias, rowmask, M, N, K, 1, K, mode};
     bool ok = true;
-    if (mode == tc::MODE_BF16) {
+    if (is_bf16_mode(mode)) {
       GemmWs w = carve_gemm(workspace, M, N, K, precision);
       STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_fwd: workspace %zu < %zu",
                      workspace_bytes, w.bytes);
       ok = castable(A, lda, K) && castable(W, ldw, K);
       if (ok) {
-        cast_bf16(A, lda, M, K, w.a16, s);
-        cast_bf16(W, ldw, N, K, w.w16, s);
-        p.A = w.a16; p.lda = K; p.B = w.w16; p.ldb = K;
+        cast_bf16(A, lda, M, K, w.a16, w.a16lo, s);
+        cast_bf16(W, ldw, N, K, w.w16, w.w16lo, s);
+        p.A = w.a16; p.lda = K; p.B = w.w16; p.ldb = K; p.A_lo = w.a16lo; p.B_lo = w.w16lo;
       }
     }
     if (ok && tc::eligible(p)) {
@@ -408,15 +429,15 @@ extern "C" int stinet_linear_dgrad(const float* dC, int64_t ldc, const float* W,
   if (mode >= 0) {
     tc::Problem p{dC, ldc, false, W, ldw, true, dA, lda, nullptr, nullptr, M, K, N, 1, N, mode};
     bool ok = true;
-    if (mode == tc::MODE_BF16) {
+    if (is_bf16_mode(mode)) {
       GemmWs w = carve_gemm(workspace, M, N, K, precision);
       STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_dgrad: workspace %zu < %zu",
                      workspace_bytes, w.bytes);
       ok = castable(dC, ldc, N) && castable(W, ldw, K);
       if (ok) {
-        cast_bf16(dC, ldc, M, N, w.c16, s);
-        cast_bf16(W, ldw, N, K, w.w16, s);
-        p.A = w.c16; p.lda = N; p.B = w.w16; p.ldb = K;
+        cast_bf16(dC, ldc, M, N, w.c16, w.c16lo, s);
+        cast_bf16(W, ldw, N, K, w.w16, w.w16lo, s);
+        p.A = w.c16; p.lda = N; p.B = w.w16; p.ldb = K; p.A_lo = w.c16lo; p.B_lo = w.w16lo;
       }
     }
     if (ok && tc::eligible(p)) {
@@ -459,12 +480,12 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
     tc::Problem p{dC, ldc, true, A, lda, true, sp.splits == 1 ? dW : w.splitk, sp.splits == 1 ? ldw : K,
                   nullptr, nullptr, N, K, M, sp.splits, sp.t_per, mode};
     bool ok = true;
-    if (mode == tc::MODE_BF16) {
+    if (is_bf16_mode(mode)) {
       ok = castable(dC, ldc, N) && castable(A, lda, K);
       if (ok) {
-        cast_bf16(dC, ldc, M, N, w.c16, s);
-        cast_bf16(A, lda, M, K, w.a16, s);
-        p.A = w.c16; p.lda = N; p.B = w.a16; p.ldb = K;
+        cast_bf16(dC, ldc, M, N, w.c16, w.c16lo, s);
+        cast_bf16(A, lda, M, K, w.a16, w.a16lo, s);
+        p.A = w.c16; p.lda = N; p.B = w.a16; p.ldb = K; p.A_lo = w.c16lo; p.B_lo = w.a16lo;
       }
     }
     if (ok && tc::eligible(p)) {

@@ -20,7 +20,10 @@
 //   TF32X3 : fp32 storage, every product evaluated as  hi*hi + hi*lo + lo*hi  on kind::tf32 with fp32 accumulation --
 //            error ~2^-22 per product, i.e. fp32-class, which the 1e-5 parity bar against the reference needs;
 //   TF32X1 : fp32 storage, one kind::tf32 pass (operands truncated by the tensor core);
-//   BF16   : bf16 storage (the caller casts), kind::f16 with fp32 accumulation -- the 2e-2 bar of the bf16 mode.
+//   BF16   : bf16 storage (the caller casts), kind::f16 with fp32 accumulation -- 2e-2 per operator;
+//   BF16X3 : the caller splits every fp32 operand into two bf16 planes x = hi + lo in HBM; TMA loads all four tiles
+//            and the products are evaluated as  hi*hi + hi*lo + lo*hi  on kind::f16 (error ~2^-16 per product) --
+//            the mode that keeps a whole deep network within 2e-2 while running bf16 tiles only.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -186,8 +189,10 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 
 template <int BN, int MODE>
 struct Cfg {
-  static constexpr bool kBf16 = MODE == MODE_BF16;
-  static constexpr bool kSplit = MODE == MODE_TF32X3;
+  static constexpr bool kBf16 = MODE == MODE_BF16 || MODE == MODE_BF16X3;
+  static constexpr bool kConv = MODE == MODE_TF32X3;               // operand split done in smem by the split warps
+  static constexpr bool kPre = MODE == MODE_BF16X3;                // operand split done by the caller in HBM
+  static constexpr bool kSplit = kConv || kPre;                    // stage holds hi and lo tiles, three MMAs per k-step
   static constexpr int kElemBytes = kBf16 ? 2 : 4;
   static constexpr int BKE = kRowBytes / kElemBytes;  // reduction elements per stage: 32 fp32 / 64 bf16
   static constexpr int MNE = kRowBytes / kElemBytes;  // MN elements per swizzle row of an MN-major operand
@@ -200,7 +205,7 @@ struct Cfg {
   static constexpr int kStagesRaw = (227 * 1024 - 1024 - (int)kStagingBytes - (int)kBarBytes) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   // two accumulator buffers of BN columns; fp32 mode doubles that for the separate correction-term accumulators
-  static constexpr uint32_t kTmemCols = (kSplit ? 4 : 2) * BN;
+  static constexpr uint32_t kTmemCols = (kConv ? 4 : 2) * BN;
   static constexpr int kEpiCols = BN / 2;             // accumulator columns owned by one epilogue warp
   // fp32 mode: the tensor core adds into its fp32 accumulator with truncation, so the error of a long reduction
   // grows linearly with K (measured: ~5e-9 * K relative).  Every kPromote k-blocks (128 reduction elements) the
@@ -210,7 +215,8 @@ struct Cfg {
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcArgs g) {
   using C_ = Cfg<BN, MODE>;
   constexpr bool kBf16 = C_::kBf16;
   constexpr int kStages = C_::kStages;
@@ -233,6 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (C_::kPre) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(conv_bar(s), 32 * kConvWarps);
@@ -275,23 +285,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const Unit w = decode(u);
         for (int kb = 0; kb < w.nkb; ++kb) {
           { DBG_T0(); mbar_wait(empty_bar(s), ph ^ 1u); DBG_ADD(0); }
-          mbar_expect_tx(full_bar(s), C_::kLoadBytes);
+          mbar_expect_tx(full_bar(s), (C_::kPre ? 2u : 1u) * C_::kLoadBytes);
           const int t0 = w.t_begin + kb * C_::BKE;
-          const uint32_t a_dst = base + s * C_::kStageBytes;
-          const uint32_t b_dst = a_dst + C_::kABytes;
-          if (!A_MN) {
-            tma_load_2d(a_dst, &tmA, t0, w.i0, full_bar(s));
-          } else {
 #pragma unroll
-            for (int b = 0; b < BM / C_::MNE; ++b)
-              tma_load_2d(a_dst + b * (C_::BKE * kRowBytes), &tmA, w.i0 + b * C_::MNE, t0, full_bar(s));
-          }
-          if (!B_MN) {
-            tma_load_2d(b_dst, &tmB, t0, w.j0, full_bar(s));
-          } else {
+          for (int plane = 0; plane < (C_::kPre ? 2 : 1); ++plane) {
+            const CUtensorMap* mA = plane ? &tmA2 : &tmA;
+            const CUtensorMap* mB = plane ? &tmB2 : &tmB;
+            const uint32_t a_dst = base + s * C_::kStageBytes + plane * C_::kLoadBytes;
+            const uint32_t b_dst = a_dst + C_::kABytes;
+            if (!A_MN) {
+              tma_load_2d(a_dst, mA, t0, w.i0, full_bar(s));
+            } else {
 #pragma unroll
-            for (int b = 0; b < BN / C_::MNE; ++b)
-              tma_load_2d(b_dst + b * (C_::BKE * kRowBytes), &tmB, w.j0 + b * C_::MNE, t0, full_bar(s));
+              for (int b = 0; b < BM / C_::MNE; ++b)
+                tma_load_2d(a_dst + b * (C_::BKE * kRowBytes), mA, w.i0 + b * C_::MNE, t0, full_bar(s));
+            }
+            if (!B_MN) {
+              tma_load_2d(b_dst, mB, t0, w.j0, full_bar(s));
+            } else {
+#pragma unroll
+              for (int b = 0; b < BN / C_::MNE; ++b)
+                tma_load_2d(b_dst + b * (C_::BKE * kRowBytes), mB, w.j0 + b * C_::MNE, t0, full_bar(s));
+            }
           }
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
@@ -330,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t tmem_d = tmem_base + buf * BN;
           const uint32_t tmem_s = g.split_acc ? tmem_d + 2 * BN : tmem_d;   // correction-term accumulator
           for (int kb = kb0; kb < kb1; ++kb) {
-            { DBG_T0(); mbar_wait(C_::kSplit ? conv_bar(s) : full_bar(s), ph); DBG_ADD(2); }
+            { DBG_T0(); mbar_wait(C_::kConv ? conv_bar(s) : full_bar(s), ph); DBG_ADD(2); }
             tcgen05_fence_after();
             const uint32_t a_hi = base + s * C_::kStageBytes;
             const uint32_t b_hi = a_hi + C_::kABytes;
@@ -349,9 +364,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t accumulate = (kb > kb0 || k > 0) ? 1u : 0u;
               if (C_::kSplit) {
                 const uint32_t a_lo = a_hi + C_::kLoadBytes, b_lo = b_hi + C_::kLoadBytes;
-                umma<false>(tmem_s, adesc(a_lo), bdesc(b_hi), idesc, accumulate);
-                umma<false>(tmem_s, adesc(a_hi), bdesc(b_lo), idesc, 1u);
-                umma<false>(tmem_d, adesc(a_hi), bdesc(b_hi), idesc, g.split_acc ? accumulate : 1u);
+                umma<kBf16>(tmem_s, adesc(a_lo), bdesc(b_hi), idesc, accumulate);
+                umma<kBf16>(tmem_s, adesc(a_hi), bdesc(b_lo), idesc, 1u);
+                umma<kBf16>(tmem_d, adesc(a_hi), bdesc(b_hi), idesc, g.split_acc ? accumulate : 1u);
               } else {
                 umma<kBf16>(tmem_d, adesc(a_hi), bdesc(b_hi), idesc, accumulate);
               }
@@ -373,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp < kEpiWarp0) {
     // ===== operand split (fp32 mode): x = hi + lo, hi = x rounded to TF32 (written in place), lo = x - hi (exact in
     // fp32; the tensor core keeps its top 11 significand bits).  Element-wise, so the swizzled layouts are untouched.
-    if (C_::kSplit) {
+    if (C_::kConv) {
       const int ct = threadIdx.x - 64;
       constexpr int kChunks = C_::kLoadBytes / 16;
       int s = 0;
@@ -428,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cc = 0; cc < EC; cc += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + cc, r);
-          if (C_::kSplit && g.split_acc) {
+          if (C_::kConv && g.split_acc) {
             uint32_t r2[32];
             tmem_ld32(taddr + 2 * BN + cc, r2);
 #pragma unroll
@@ -539,6 +554,16 @@ static int launch(const Problem& p, cudaStream_t s) {
   else rc = make_map(&tmB, p.B, p.J, p.T, p.ldb, bf16, C_::MNE, C_::BKE,
                      bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (C_::kPre) {
+    STINET_REQUIRE(p.A_lo && p.B_lo, STINET_ERR_ARG, "gemm_tc: bf16x3 needs the lo planes of both operands");
+    if (!A_MN) rc = make_map(&tmA2, p.A_lo, p.T, p.I, p.lda, true, C_::BKE, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_map(&tmA2, p.A_lo, p.I, p.T, p.lda, true, C_::MNE, C_::BKE, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (!B_MN) rc = make_map(&tmB2, p.B_lo, p.T, p.J, p.ldb, true, C_::BKE, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_map(&tmB2, p.B_lo, p.J, p.T, p.ldb, true, C_::MNE, C_::BKE, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE>;
   static bool attr_set = false;  // per instantiation; idempotent, so a race only repeats the call
   if (!attr_set) {
@@ -557,9 +582,9 @@ static int launch(const Problem& p, cudaStream_t s) {
   static const int env_split = [] { const char* e = getenv("STINET_TC_SPLITACC"); return e ? atoi(e) : 1; }();
   TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split,
            tiles_j, tiles_i * tiles_j, (int)units,
-           C_::kSplit ? (env_promote > 0 ? env_promote : 4) : (1 << 28), C_::kSplit ? env_split : 0};
+           C_::kConv ? (env_promote > 0 ? env_promote : 4) : (1 << 28), C_::kConv ? env_split : 0};
   const unsigned grid = (unsigned)(units < kSMs ? units : kSMs);   // persistent: one CTA per SM walks the work units
-  K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, g));
+  K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, g));
   return check_launch("gemm_tc");
 }
 
@@ -579,10 +604,11 @@ static int launch_major(const Problem& p, cudaStream_t s) {
 }
 
 bool eligible(const Problem& p) {
-  const int esz = p.mode == MODE_BF16 ? 2 : 4;
+  const int esz = (p.mode == MODE_BF16 || p.mode == MODE_BF16X3) ? 2 : 4;
   const int64_t align_elems = 16 / esz;
   if (p.I <= 0 || p.J <= 0 || p.T <= 0) return false;
   if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
+  if (p.mode == MODE_BF16X3 && (!p.A_lo || !p.B_lo || !aligned16(p.A_lo) || !aligned16(p.B_lo))) return false;
   if (p.lda % align_elems || p.ldb % align_elems) return false;
   if (p.ldc % 4 || p.J % 4) return false;
   if (p.bias && !aligned16(p.bias)) return false;
@@ -597,6 +623,7 @@ int run(const Problem& p, cudaStream_t s) {
     case MODE_TF32X3: return launch_major<MODE_TF32X3>(p, s);
     case MODE_TF32X1: return launch_major<MODE_TF32X1>(p, s);
     case MODE_BF16: return launch_major<MODE_BF16>(p, s);
+    case MODE_BF16X3: return launch_major<MODE_BF16X3>(p, s);
   }
   set_error("gemm_tc: unknown mode %d", p.mode);
   return STINET_ERR_ARG;

