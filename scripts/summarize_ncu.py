@@ -1,7 +1,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
 
     python scripts/summarize_ncu.py launches gpurun_out/launches_X.csv profiles/r1_X_launches.md
-    python scripts/summarize_ncu.py full     gpurun_out/prof_X.ncu-rep  profiles/r1_X_full.md
+    python scripts/summarize_ncu.py full     gpurun_out/prof_X.ncu-rep|prof_X_raw.csv  profiles/r1_X_full.md
 """
 import collections
 import csv
@@ -44,7 +44,12 @@ WANT = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
 
 
 def full(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: a .ncu-rep, or the `ncu -i rep --page raw --csv` dump of one made on the GPU box (reps over ~20 MB do not
+    # fit gpurun_out/'s 64 MiB cap, so scripts/gpu_round.sh converts there)
+    if src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     cols = [(hdr.index(m), lab) for m, lab in WANT if m in hdr]
