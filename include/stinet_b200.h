@@ -99,6 +99,15 @@ int stinet_edge_message_bwd_source(const float* P, int64_t ldp, const float* Q, 
                                    const int32_t* col_s, int64_t n_rows, int64_t hidden, float* dQ, int64_t lddq,
                                    stinet_stream_t stream);
 
+/* Parameters of the hoisted first layer from nn.0's own W [hidden, kin] / b [hidden] (kin = 2*din, or din for
+ * EdgeConvTransInv):  Wcat [2*hidden, din] = [Wa - Wb ; Wb]  (trans_inv: [-W ; W]),  bcat [2*hidden] = [b ; 0]
+ * (b / bcat nullable together), and the matching gradient fold  dW = [dP-part | dQ-part - dP-part], db = dbcat[:hidden].
+ * Wcat / dWcat are dense (ld = din). */
+int stinet_edgeconv_hoist_fwd(const float* W, int64_t ldw, const float* b, int64_t hidden, int64_t din, int trans_inv,
+                              float* Wcat, float* bcat, stinet_stream_t stream);
+int stinet_edgeconv_hoist_bwd(const float* dWcat, const float* dbcat, int64_t hidden, int64_t din, int trans_inv,
+                              float* dW, int64_t ldw, float* db, stinet_stream_t stream);
+
 /* ---- trace-map pooling / unpooling (replaces SurfaceTextureInpaintingNet._pooling / _unpooling,
  * models/surfacetextureinpaintingnet.py:382-391 = torch_scatter.scatter_max / scatter_mean / x[trace]).
  * Cluster CSR: rowptr_c[n_coarse+1], member[n_fine] = fine vertex ids grouped by cluster in ascending order
@@ -136,6 +145,15 @@ int stinet_segnorm_stats(const float* x, int64_t ldx, int64_t n_rows, int64_t ch
                          int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, const int32_t* gid,
                          float eps, float* mean, float* rstd, void* workspace, size_t workspace_bytes,
                          stinet_stream_t stream);
+/* One-call forward for batches whose slices ARE the graphs (equal-size batches, and batch=None = one slice; the only
+ * cases the reference trains on):  out = residual + act((x - mean[s]) * rstd[s]),  mean / rstd [n_seg, channels] are
+ * written for the backward.  Slices of at most 16384 rows run as ONE kernel (a thread-block cluster per (slice,
+ * 32-channel slab), partial sums exchanged through distributed shared memory in rank order, rows kept in registers
+ * between the passes when they fit); longer slices run stats + a slice-indexed apply kernel. */
+int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
+                       int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, float eps,
+                       const float* residual, int64_t ldr, int act, float* out, int64_t ldo, float* mean, float* rstd,
+                       void* workspace, size_t workspace_bytes, stinet_stream_t stream);
 /* out = residual + act((x - mean[g]) * rstd[g])   (residual nullable; act = STINET_ACT_*): the tail of
  * GraphResnetBlock.forward, models/surfacetextureinpaintingnet.py:510-521.  g = gid[r] (NULL: segment 0);
  * mean == rstd == NULL: identity norm (norm_type 'none', :257-263). */
@@ -144,7 +162,8 @@ int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows, int64_t ch
                          float* out, int64_t ldo, stinet_stream_t stream);
 /* backward of out = act(norm(x)):  dx = rstd*(dz - mean_s(dz) - yhat*mean_s(dz*yhat)), dz = dout*act'(yhat).
  * Requires slices == true segments (gid constant on every slice); otherwise STINET_ERR_UNSUPPORTED is the
- * caller's job to raise (the library cannot see it without a sync). */
+ * caller's job to raise (the library cannot see it without a sync).  gid == NULL: a row uses the statistics of the
+ * slice that contains it (single cluster kernel for slices of at most 16384 rows, as in stinet_segnorm_fwd). */
 int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows, int64_t channels,
                        int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt,
                        const int32_t* gid, const float* mean, const float* rstd, int act, float* dx, int64_t lddx,

@@ -3,7 +3,16 @@
 //           two-pass as well), each = per-chunk partials + a fixed-order finalize;
 //   apply : out = residual + act((x - mean[g]) * rstd[g])            (one read of x, one write)
 //   bwd   : one reduction pass (sum dz, sum dz*yhat) + one apply pass.
+// Slices that are true segments (gid == NULL) get two faster forms:
+//   * short slices: ONE kernel per direction.  A thread-block cluster owns a (slice, 32-channel slab) pair, its CTAs
+//     split the rows, per-CTA partial sums are exchanged through distributed shared memory in rank order
+//     (deterministic), and -- when the CTA's rows fit -- the rows stay in registers between the passes, so x is read
+//     from HBM once;
+//   * long slices: the same partial/finalize reductions, then slice-indexed apply kernels in which a thread keeps one
+//     float4 column (mean / rstd loaded once) and streams rows four at a time.
+#include <cooperative_groups.h>
 #include "common.cuh"
+namespace cg = cooperative_groups;
 
 namespace stinet {
 
@@ -25,9 +34,10 @@ struct NormArgs {
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kNormThreads) seg_colreduce_kernel(NormArgs a) {
   constexpr int W = VEC ? 4 : 1;
+  constexpr int U = 4;                               // rows in flight per thread
   const int groups = a.channels / W;
   const int txw = min(groups, kTileGroups);         // threads along channels
-  const int tyn = kNormThreads / txw;                // rows in flight
+  const int tyn = kNormThreads / txw;                // row lanes
   const int tx = threadIdx.x % txw, ty = threadIdx.x / txw;
   const int s = blockIdx.y;
   const int grp = blockIdx.z * kTileGroups + tx;
@@ -37,41 +47,56 @@ __global__ void __launch_bounds__(kNormThreads) seg_colreduce_kernel(NormArgs a)
 #pragma unroll
   for (int w = 0; w < W; ++w) acc0[w] = acc1[w] = 0.f;
   if (grp < groups && ty < tyn) {
-    for (int r = r0 + ty; r < r1; r += tyn) {
-      float v[W], d[W], m[W], rs[W];
-      const int g = a.gid ? a.gid[r] : s;
-      if (VEC) {
-        float4 t = reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[grp];
-        v[0] = t.x; v[1 % W] = t.y; v[2 % W] = t.z; v[3 % W] = t.w;
-      } else {
-        v[0] = a.x[(int64_t)r * a.ldx + grp];
-      }
-      if (MODE != MODE_SUM) {
+    // statistics of the slice itself (gid == NULL): loaded once per thread instead of once per row
+    float ms[W], rss[W];
 #pragma unroll
-        for (int w = 0; w < W; ++w) m[w] = a.mean ? a.mean[(int64_t)g * a.channels + grp * W + w] : 0.f;
-      }
-      if (MODE == MODE_BWD) {
+    for (int w = 0; w < W; ++w) {
+      ms[w] = (MODE != MODE_SUM && !a.gid && a.mean) ? a.mean[(int64_t)s * a.channels + grp * W + w] : 0.f;
+      rss[w] = (MODE == MODE_BWD && !a.gid && a.rstd) ? a.rstd[(int64_t)s * a.channels + grp * W + w] : 1.f;
+    }
+    for (int rb = r0 + ty; rb < r1; rb += U * tyn) {
+      float v[U][W], d[U][W];
+      int g[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rb + u * tyn;
+        const bool ok = r < r1;
+        g[u] = (MODE != MODE_SUM && a.gid && ok) ? a.gid[r] : s;
         if (VEC) {
-          float4 t = reinterpret_cast<const float4*>(a.dout + (int64_t)r * a.ldg)[grp];
-          d[0] = t.x; d[1 % W] = t.y; d[2 % W] = t.z; d[3 % W] = t.w;
+          float4 t = ok ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[grp] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u][0] = t.x; v[u][1 % W] = t.y; v[u][2 % W] = t.z; v[u][3 % W] = t.w;
         } else {
-          d[0] = a.dout[(int64_t)r * a.ldg + grp];
+          v[u][0] = ok ? a.x[(int64_t)r * a.ldx + grp] : 0.f;
         }
-#pragma unroll
-        for (int w = 0; w < W; ++w) rs[w] = a.rstd ? a.rstd[(int64_t)g * a.channels + grp * W + w] : 1.f;
+        if (MODE == MODE_BWD) {
+          if (VEC) {
+            float4 t = ok ? reinterpret_cast<const float4*>(a.dout + (int64_t)r * a.ldg)[grp] : make_float4(0.f, 0.f, 0.f, 0.f);
+            d[u][0] = t.x; d[u][1 % W] = t.y; d[u][2 % W] = t.z; d[u][3 % W] = t.w;
+          } else {
+            d[u][0] = ok ? a.dout[(int64_t)r * a.ldg + grp] : 0.f;
+          }
+        }
       }
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        if (MODE == MODE_SUM) {
-          acc0[w] += v[w];
-        } else if (MODE == MODE_CSQ) {
-          const float c = v[w] - m[w];
-          acc0[w] += c * c;
-        } else {
-          const float yh = (v[w] - m[w]) * rs[w];
-          const float dz = (a.act == STINET_ACT_ELU) ? d[w] * elu1_grad(yh) : d[w];
-          acc0[w] += dz;
-          acc1[w] += dz * yh;
+      for (int u = 0; u < U; ++u) {
+        if (rb + u * tyn < r1) {                     // rows are accumulated in ascending order, as before
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            float m = ms[w], rs = rss[w];
+            if (MODE != MODE_SUM && a.gid && a.mean) m = a.mean[(int64_t)g[u] * a.channels + grp * W + w];
+            if (MODE == MODE_BWD && a.gid && a.rstd) rs = a.rstd[(int64_t)g[u] * a.channels + grp * W + w];
+            if (MODE == MODE_SUM) {
+              acc0[w] += v[u][w];
+            } else if (MODE == MODE_CSQ) {
+              const float c = v[u][w] - m;
+              acc0[w] += c * c;
+            } else {
+              const float yh = (v[u][w] - m) * rs;
+              const float dz = (a.act == STINET_ACT_ELU) ? d[u][w] * elu1_grad(yh) : d[u][w];
+              acc0[w] += dz;
+              acc1[w] += dz * yh;
+            }
+          }
         }
       }
     }
@@ -209,6 +234,349 @@ segnorm_bwd_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// slices == segments: slice-indexed apply kernels (long slices) and the single-kernel cluster forms (short slices)
+
+constexpr int kApplyU = 4;  // rows in flight per thread
+
+// grid (row chunks, slices, 32-group slabs); a thread owns one float4 column and streams rows kApplyU at a time.
+//   BWD = false: out = res + act((x - mean[s]) * rstd[s])                                   (aux = residual, nullable)
+//   BWD = true : dx  = rstd[s] * (dz - s1[s] - yhat * s2[s]),  dz = dout * act'(yhat)      (aux = dout)
+template <bool BWD>
+__global__ void __launch_bounds__(kNormThreads)
+segnorm_slice_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ aux, int64_t lda,
+                           const int32_t* __restrict__ slice_ptr, int channels, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ s1, const float* __restrict__ s2,
+                           int act, float* __restrict__ out, int64_t ldo) {
+  const int groups = channels >> 2;
+  const int txw = min(groups, kTileGroups);
+  const int tyn = kNormThreads / txw;
+  const int tx = threadIdx.x % txw, ty = threadIdx.x / txw;
+  const int s = blockIdx.y;
+  const int grp = blockIdx.z * kTileGroups + tx;
+  if (grp >= groups || ty >= tyn) return;
+  const int rows_per_cta = tyn * kApplyU * 2;
+  const int r0 = slice_ptr[s] + blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, slice_ptr[s + 1]);
+  const int64_t sc = (int64_t)s * channels + grp * 4;
+  const float4 m = *reinterpret_cast<const float4*>(mean + sc);
+  const float4 rs = *reinterpret_cast<const float4*>(rstd + sc);
+  float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+  if (BWD) {
+    a1 = *reinterpret_cast<const float4*>(s1 + sc);
+    a2 = *reinterpret_cast<const float4*>(s2 + sc);
+  }
+  const float mv[4] = {m.x, m.y, m.z, m.w}, rv[4] = {rs.x, rs.y, rs.z, rs.w};
+  const float p1[4] = {a1.x, a1.y, a1.z, a1.w}, p2[4] = {a2.x, a2.y, a2.z, a2.w};
+  for (int rb = r0 + ty; rb < r1; rb += kApplyU * tyn) {
+    float4 v[kApplyU], w[kApplyU];
+#pragma unroll
+    for (int u = 0; u < kApplyU; ++u) {
+      const int r = rb + u * tyn;
+      v[u] = w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < r1) {
+        v[u] = ld_stream(reinterpret_cast<const float4*>(x + (int64_t)r * ldx) + grp);
+        if (aux) w[u] = ld_stream(reinterpret_cast<const float4*>(aux + (int64_t)r * lda) + grp);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kApplyU; ++u) {
+      const int r = rb + u * tyn;
+      if (r < r1) {
+        const float xv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const float wv[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float yh = (xv[q] - mv[q]) * rv[q];
+          if (BWD) {
+            const float dz = (act == STINET_ACT_ELU) ? wv[q] * elu1_grad(yh) : wv[q];
+            o[q] = rv[q] * (dz - p1[q] - yh * p2[q]);
+          } else {
+            o[q] = (act == STINET_ACT_ELU) ? elu1(yh) : yh;
+            if (aux) o[q] += wv[q];
+          }
+        }
+        st_stream(reinterpret_cast<float4*>(out + (int64_t)r * ldo) + grp, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+  }
+}
+
+constexpr int kFusedG = 8;        // float4 columns per CTA: a 32-channel slab = one 128-byte line per row
+constexpr int kFusedLanes = 32;   // row lanes per CTA (256 threads)
+constexpr int kFusedRR = 8;       // rows a thread can keep in registers -> 256 rows per CTA
+constexpr int kFusedMaxCluster = 8;
+static_assert(kFusedG * kFusedLanes == kNormThreads, "fused norm kernels: 8 columns x 32 row lanes");
+
+struct FusedArgs {
+  const float* x; int64_t ldx;
+  const float* aux; int64_t lda;       // fwd: residual (nullable); bwd: dout
+  const int32_t* slice_ptr; const float* cnt;
+  float* mean; float* rstd;            // fwd: outputs; bwd: inputs
+  float* out; int64_t ldo;
+  int channels; int act; float eps;
+};
+
+__device__ __forceinline__ float4 f4add(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// Sum of `v` over the row lanes of this CTA and then over the CTAs of the cluster, both in a fixed order.
+// `sm` is a 256-entry scratch, `part` a per-pass 8-entry exchange buffer (never reused, so one cluster.sync suffices).
+__device__ __forceinline__ float4 cluster_column_sum(float4 v, float4* sm, float4* part, cg::cluster_group& cluster) {
+  const int tx = threadIdx.x & (kFusedG - 1), ty = threadIdx.x >> 3;
+  __syncthreads();                      // previous users of sm are done
+  sm[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int off = kFusedLanes / 2; off >= 1; off >>= 1) {
+    if (ty < off) sm[threadIdx.x] = f4add(sm[threadIdx.x], sm[threadIdx.x + off * kFusedG]);
+    __syncthreads();
+  }
+  if (ty == 0) part[tx] = sm[tx];
+  cluster.sync();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  const unsigned cs = cluster.num_blocks();
+  for (unsigned k = 0; k < cs; ++k) t = f4add(t, cluster.map_shared_rank(part, k)[tx]);
+  return t;
+}
+
+// RR > 0: the CTA's rows (<= 32*RR) are loaded once and kept in registers; RR == 0: every pass re-reads them (L2).
+template <int RR>
+__global__ void __launch_bounds__(kNormThreads) segnorm_fused_fwd_kernel(FusedArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float4 sm[kNormThreads];
+  __shared__ float4 part_a[kFusedG], part_b[kFusedG];
+  const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int tx = threadIdx.x & (kFusedG - 1), ty = threadIdx.x >> 3;
+  const int s = blockIdx.y;
+  const int c4 = (blockIdx.x / cs) * kFusedG + tx;
+  const bool col = c4 < (a.channels >> 2);
+  const int b = a.slice_ptr[s], e = a.slice_ptr[s + 1];
+  const int per = (e - b + cs - 1) / cs;
+  const int r0 = b + rank * per, r1 = min(r0 + per, e);
+  const float cnt = a.cnt[s];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int NR = RR > 0 ? RR : 1;
+  float4 v[NR];
+  float4 acc = zero;
+  if (RR > 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + ty + i * kFusedLanes;
+      v[i] = (col && r < r1) ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : zero;
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc = f4add(acc, v[i]);
+  } else if (col) {
+    for (int rb = r0 + ty; rb < r1; rb += 4 * kFusedLanes) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        t[u] = r < r1 ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = f4add(acc, t[u]);
+    }
+  }
+  float4 tot = cluster_column_sum(acc, sm, part_a, cluster);
+  const float4 m = make_float4(tot.x / cnt, tot.y / cnt, tot.z / cnt, tot.w / cnt);
+  acc = zero;
+  if (RR > 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + ty + i * kFusedLanes;
+      if (col && r < r1) {
+        const float dx = v[i].x - m.x, dy = v[i].y - m.y, dz = v[i].z - m.z, dw = v[i].w - m.w;
+        acc.x += dx * dx; acc.y += dy * dy; acc.z += dz * dz; acc.w += dw * dw;
+      }
+    }
+  } else if (col) {
+    for (int rb = r0 + ty; rb < r1; rb += 4 * kFusedLanes) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        t[u] = r < r1 ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : m;   // (m - m)^2 adds exactly 0
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float dx = t[u].x - m.x, dy = t[u].y - m.y, dz = t[u].z - m.z, dw = t[u].w - m.w;
+        acc.x += dx * dx; acc.y += dy * dy; acc.z += dz * dz; acc.w += dw * dw;
+      }
+    }
+  }
+  tot = cluster_column_sum(acc, sm, part_b, cluster);
+  const float4 rs = make_float4(1.f / sqrtf(tot.x / cnt + a.eps), 1.f / sqrtf(tot.y / cnt + a.eps),
+                                1.f / sqrtf(tot.z / cnt + a.eps), 1.f / sqrtf(tot.w / cnt + a.eps));
+  if (rank == 0 && ty == 0 && col) {
+    reinterpret_cast<float4*>(a.mean + (int64_t)s * a.channels)[c4] = m;
+    reinterpret_cast<float4*>(a.rstd + (int64_t)s * a.channels)[c4] = rs;
+  }
+  auto finish = [&](const float4& xv, int r) {
+    float4 o = make_float4((xv.x - m.x) * rs.x, (xv.y - m.y) * rs.y, (xv.z - m.z) * rs.z, (xv.w - m.w) * rs.w);
+    if (a.act == STINET_ACT_ELU) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
+    if (a.aux) o = f4add(o, reinterpret_cast<const float4*>(a.aux + (int64_t)r * a.lda)[c4]);
+    reinterpret_cast<float4*>(a.out + (int64_t)r * a.ldo)[c4] = o;
+  };
+  if (RR > 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + ty + i * kFusedLanes;
+      if (col && r < r1) finish(v[i], r);
+    }
+  } else if (col) {
+    for (int rb = r0 + ty; rb < r1; rb += 4 * kFusedLanes) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        t[u] = r < r1 ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        if (r < r1) finish(t[u], r);
+      }
+    }
+  }
+  cluster.sync();   // no CTA may exit while a peer can still read its exchange buffers
+}
+
+template <int RR>
+__global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float4 sm[kNormThreads];
+  __shared__ float4 part_a[kFusedG], part_b[kFusedG];
+  const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int tx = threadIdx.x & (kFusedG - 1), ty = threadIdx.x >> 3;
+  const int s = blockIdx.y;
+  const int c4 = (blockIdx.x / cs) * kFusedG + tx;
+  const bool col = c4 < (a.channels >> 2);
+  const int b = a.slice_ptr[s], e = a.slice_ptr[s + 1];
+  const int per = (e - b + cs - 1) / cs;
+  const int r0 = b + rank * per, r1 = min(r0 + per, e);
+  const float cnt = a.cnt[s];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 m = col ? reinterpret_cast<const float4*>(a.mean + (int64_t)s * a.channels)[c4] : zero;
+  const float4 rs = col ? reinterpret_cast<const float4*>(a.rstd + (int64_t)s * a.channels)[c4] : zero;
+  const bool elu = a.act == STINET_ACT_ELU;
+  // (yhat, dz) of one element quad
+  auto prep = [&](const float4& xv, const float4& dv, float4& yh, float4& dz) {
+    yh = make_float4((xv.x - m.x) * rs.x, (xv.y - m.y) * rs.y, (xv.z - m.z) * rs.z, (xv.w - m.w) * rs.w);
+    dz = dv;
+    if (elu) { dz.x *= elu1_grad(yh.x); dz.y *= elu1_grad(yh.y); dz.z *= elu1_grad(yh.z); dz.w *= elu1_grad(yh.w); }
+  };
+  constexpr int NR = RR > 0 ? RR : 1;
+  float4 yhc[NR], dzc[NR];
+  float4 acc0 = zero, acc1 = zero;
+  if (RR > 0) {
+    float4 xv[NR], dv[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + ty + i * kFusedLanes;
+      const bool ok = col && r < r1;
+      xv[i] = ok ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : m;
+      dv[i] = ok ? reinterpret_cast<const float4*>(a.aux + (int64_t)r * a.lda)[c4] : zero;
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      prep(xv[i], dv[i], yhc[i], dzc[i]);     // padded rows: yhat = 0, dz = 0 -> contribute exactly 0
+      acc0 = f4add(acc0, dzc[i]);
+      acc1.x += dzc[i].x * yhc[i].x; acc1.y += dzc[i].y * yhc[i].y; acc1.z += dzc[i].z * yhc[i].z; acc1.w += dzc[i].w * yhc[i].w;
+    }
+  } else if (col) {
+    for (int rb = r0 + ty; rb < r1; rb += 4 * kFusedLanes) {
+      float4 xv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        xv[u] = r < r1 ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : m;
+        dv[u] = r < r1 ? reinterpret_cast<const float4*>(a.aux + (int64_t)r * a.lda)[c4] : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 yh, dz;
+        prep(xv[u], dv[u], yh, dz);
+        acc0 = f4add(acc0, dz);
+        acc1.x += dz.x * yh.x; acc1.y += dz.y * yh.y; acc1.z += dz.z * yh.z; acc1.w += dz.w * yh.w;
+      }
+    }
+  }
+  const float4 t0 = cluster_column_sum(acc0, sm, part_a, cluster);
+  const float4 t1 = cluster_column_sum(acc1, sm, part_b, cluster);
+  const float4 s1 = make_float4(t0.x / cnt, t0.y / cnt, t0.z / cnt, t0.w / cnt);
+  const float4 s2 = make_float4(t1.x / cnt, t1.y / cnt, t1.z / cnt, t1.w / cnt);
+  auto finish = [&](const float4& yh, const float4& dz, int r) {
+    const float4 o = make_float4(rs.x * (dz.x - s1.x - yh.x * s2.x), rs.y * (dz.y - s1.y - yh.y * s2.y),
+                                 rs.z * (dz.z - s1.z - yh.z * s2.z), rs.w * (dz.w - s1.w - yh.w * s2.w));
+    reinterpret_cast<float4*>(a.out + (int64_t)r * a.ldo)[c4] = o;
+  };
+  if (RR > 0) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int r = r0 + ty + i * kFusedLanes;
+      if (col && r < r1) finish(yhc[i], dzc[i], r);
+    }
+  } else if (col) {
+    for (int rb = r0 + ty; rb < r1; rb += 4 * kFusedLanes) {
+      float4 xv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        xv[u] = r < r1 ? reinterpret_cast<const float4*>(a.x + (int64_t)r * a.ldx)[c4] : m;
+        dv[u] = r < r1 ? reinterpret_cast<const float4*>(a.aux + (int64_t)r * a.lda)[c4] : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * kFusedLanes;
+        if (r < r1) {
+          float4 yh, dz;
+          prep(xv[u], dv[u], yh, dz);
+          finish(yh, dz, r);
+        }
+      }
+    }
+  }
+  cluster.sync();
+}
+
+// Launch geometry of the single-kernel forms: the smallest cluster (1, 2, 4, 8 CTAs) whose CTAs can keep their rows
+// in registers, the largest one otherwise.  Slices longer than kFusedMaxRows use the multi-kernel path.
+constexpr int64_t kFusedMaxRows = 16384;
+struct FusedPlan { int cluster; bool cached; };
+static FusedPlan fused_plan(int64_t max_seg_rows) {
+  int cs = 1;
+  while (cs < kFusedMaxCluster && ceil_div(max_seg_rows, cs) > kFusedRR * kFusedLanes) cs *= 2;
+  return FusedPlan{cs, ceil_div(max_seg_rows, cs) <= kFusedRR * kFusedLanes};
+}
+
+template <typename Kern>
+static int launch_fused(Kern kern, const FusedArgs& a, int64_t n_seg, int cluster, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  const unsigned slabs = (unsigned)ceil_div(a.channels >> 2, kFusedG);
+  cfg.gridDim = dim3(slabs * cluster, (unsigned)n_seg, 1);
+  cfg.blockDim = dim3(kNormThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+  count_launch();
+  if (e != cudaSuccess) {
+    set_error("segnorm fused launch: %s", cudaGetErrorString(e));
+    return STINET_ERR_CUDA;
+  }
+  return STINET_OK;
+}
+
 struct NormWs {
   float *part0, *part1, *s1, *s2;
   size_t bytes;
@@ -293,6 +661,40 @@ extern "C" int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows,
   return check_launch("segnorm_apply");
 }
 
+extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
+                                  int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, float eps,
+                                  const float* residual, int64_t ldr, int act, float* out, int64_t ldo, float* mean,
+                                  float* rstd, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && slice_ptr && cnt && mean && rstd && out, STINET_ERR_ARG, "segnorm_fwd: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && channels > 0 && n_seg > 0 && n_seg <= 65535 && ldx >= channels && ldo >= channels &&
+                     (!residual || ldr >= channels),
+                 STINET_ERR_ARG, "segnorm_fwd: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const bool vec = nvec(channels, {x, out, residual, mean, rstd}, {ldx, ldo, residual ? ldr : 0});
+  if (vec && max_seg_rows <= kFusedMaxRows) {
+    const FusedPlan pl = fused_plan(max_seg_rows);
+    FusedArgs a{x, ldx, residual, ldr, slice_ptr, cnt, mean, rstd, out, ldo, (int)channels, act, eps};
+    return pl.cached ? launch_fused(segnorm_fused_fwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
+                     : launch_fused(segnorm_fused_fwd_kernel<0>, a, n_seg, pl.cluster, s);
+  }
+  int rc = stinet_segnorm_stats(x, ldx, n_rows, channels, n_seg, max_seg_rows, slice_ptr, cnt, nullptr, eps, mean, rstd,
+                                workspace, workspace_bytes, stream_);
+  if (rc != STINET_OK) return rc;
+  if (vec) {
+    const int groups = (int)(channels >> 2);
+    const int tyn = kNormThreads / (groups < kTileGroups ? groups : kTileGroups);
+    dim3 grid((unsigned)ceil_div(max_seg_rows, tyn * kApplyU * 2), (unsigned)n_seg, (unsigned)ceil_div(groups, kTileGroups));
+    K(segnorm_slice_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, residual, ldr, slice_ptr, (int)channels, mean,
+                                                                      rstd, nullptr, nullptr, act, out, ldo));
+    return check_launch("segnorm_fwd");
+  }
+  // odd widths: the per-row lookup kernel needs a graph id; a single slice uses id 0
+  STINET_REQUIRE(n_seg == 1, STINET_ERR_UNSUPPORTED, "segnorm_fwd: channel count %lld (not a multiple of 4) with %lld slices",
+                 (long long)channels, (long long)n_seg);
+  return stinet_segnorm_apply(x, ldx, n_rows, channels, nullptr, mean, rstd, residual, ldr, act, out, ldo, stream_);
+}
+
 extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows,
                                   int64_t channels, int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr,
                                   const float* cnt, const int32_t* gid, const float* mean, const float* rstd, int act,
@@ -303,8 +705,19 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
   STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldx >= channels && ldg >= channels && lddx >= channels,
                  STINET_ERR_ARG, "segnorm_bwd: bad shape");
   if (n_rows == 0) return STINET_OK;
-  const bool vec = nvec(channels, {x, dout, dx}, {ldx, ldg, lddx});
+  const bool vec = nvec(channels, {x, dout, dx, mean, rstd}, {ldx, ldg, lddx});
   const float *s1 = nullptr, *s2 = nullptr;
+  const bool by_slice = mean && !gid && vec;          // slices are the segments
+  if (mean && !gid && !vec)
+    STINET_REQUIRE(n_seg == 1, STINET_ERR_UNSUPPORTED, "segnorm_bwd: odd channel count with several slices needs gid");
+  if (by_slice && max_seg_rows <= kFusedMaxRows) {
+    STINET_REQUIRE(slice_ptr && cnt && n_seg > 0 && n_seg <= 65535, STINET_ERR_ARG, "segnorm_bwd: segments required");
+    const FusedPlan pl = fused_plan(max_seg_rows);
+    FusedArgs a{x, ldx, dout, ldg, slice_ptr, cnt, const_cast<float*>(mean), const_cast<float*>(rstd), dx, lddx,
+                (int)channels, act, 0.f};
+    return pl.cached ? launch_fused(segnorm_fused_bwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
+                     : launch_fused(segnorm_fused_bwd_kernel<0>, a, n_seg, pl.cluster, s);
+  }
   if (mean) {
     STINET_REQUIRE(slice_ptr && cnt && n_seg > 0 && n_seg <= 65535, STINET_ERR_ARG, "segnorm_bwd: segments required");
     NormWs w = carve_norm(workspace, max_seg_rows, channels, n_seg);
@@ -317,6 +730,14 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.part1, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s2));
     s1 = w.s1;
     s2 = w.s2;
+  }
+  if (by_slice) {
+    const int groups = (int)(channels >> 2);
+    const int tyn = kNormThreads / (groups < kTileGroups ? groups : kTileGroups);
+    dim3 grid2((unsigned)ceil_div(max_seg_rows, tyn * kApplyU * 2), (unsigned)n_seg, (unsigned)ceil_div(groups, kTileGroups));
+    K(segnorm_slice_apply_kernel<true><<<grid2, kNormThreads, 0, s>>>(x, ldx, dout, ldg, slice_ptr, (int)channels, mean, rstd,
+                                                                      s1, s2, act, dx, lddx));
+    return check_launch("segnorm_bwd");
   }
   const int grid = wave_grid(n_rows * (channels / (vec ? 4 : 1)), kNormThreads * 4, 8, 8);
   if (vec) K(segnorm_bwd_apply_kernel<true><<<grid, kNormThreads, 0, s>>>(x, ldx, dout, ldg, n_rows, (int)channels, gid, mean, rstd, s1, s2, act, dx, lddx));

@@ -27,6 +27,8 @@ SIGNATURES = {
     "stinet_edge_message_fwd": (I, [P, I64, P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_target": (I, [P, I64, P, I64, P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_source": (I, [P, I64, P, I64, P, I64, P, P, P, I64, I64, P, I64, P]),
+    "stinet_edgeconv_hoist_fwd": (I, [P, I64, P, I64, I64, I, P, P, P]),
+    "stinet_edgeconv_hoist_bwd": (I, [P, P, I64, I64, I, P, I64, P, P]),
     "stinet_pool_max_fwd": (I, [P, I64, P, P, I64, I64, I64, P, I64, P, P]),
     "stinet_pool_max_bwd": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_pool_mean_fwd": (I, [P, I64, P, P, I64, I64, P, I64, P]),
@@ -36,6 +38,7 @@ SIGNATURES = {
     "stinet_unpool_bwd": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_segnorm_workspace_bytes": (SZ, [I64, I64, I64]),
     "stinet_segnorm_stats": (I, [P, I64, I64, I64, I64, I64, P, P, P, F, P, P, P, SZ, P]),
+    "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, SZ, P]),
     "stinet_segnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, I64, P]),
     "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, SZ, P]),
     "stinet_gemm_workspace_bytes": (SZ, [I64, I64, I64, I]),

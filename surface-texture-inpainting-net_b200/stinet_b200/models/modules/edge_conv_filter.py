@@ -37,17 +37,8 @@ class EdgeConv(torch.nn.Module):
 
     def hoisted_first_layer(self):
         """[P | Q] weights/bias of the first Linear: W [2H, din], b [2H]."""
-        w, b = self.nn[0].weight, self.nn[0].bias
-        if self.trans_inv:                      # nn.0(x_j - x_i) = (-W) x_i + W x_j
-            wcat = torch.cat([-w, w], dim=0)
-        else:                                   # nn.0([x_i || x_j - x_i]) = (Wa - Wb) x_i + Wb x_j
-            din = w.shape[1] // 2
-            wa, wb = w[:, :din], w[:, din:]
-            wcat = torch.cat([wa - wb, wb], dim=0)
-        bcat = None
-        if b is not None:
-            bcat = torch.cat([b, torch.zeros_like(b)], dim=0)
-        return wcat, bcat
+        # trans_inv: nn.0(x_j - x_i) = (-W) x_i + W x_j;  else nn.0([x_i || x_j - x_i]) = (Wa - Wb) x_i + Wb x_j
+        return ops.edgeconv_hoist(self.nn[0].weight, self.nn[0].bias, self.trans_inv)
 
     def forward(self, x, edge_index):
         csr = as_edge_csr(edge_index, x.shape[0])

@@ -152,6 +152,46 @@ def edge_message(pq, csr):
     return EdgeMessageFn.apply(pq, csr)
 
 
+class EdgeConvHoistFn(Function):
+    """(Wcat, bcat) of the hoisted first layer from nn.0's own parameters, and the gradient fold back onto them."""
+
+    @staticmethod
+    def forward(ctx, w, b, trans_inv: bool):
+        w = _mat(w)
+        h, kin = w.shape
+        din = kin if trans_inv else kin // 2
+        assert trans_inv or kin == 2 * din
+        wcat = torch.empty((2 * h, din), dtype=torch.float32, device=w.device)
+        bcat = torch.empty((2 * h,), dtype=torch.float32, device=w.device) if b is not None else None
+        _abi.call("stinet_edgeconv_hoist_fwd", w.data_ptr(), _ld(w), _ptr(b), h, din, int(trans_inv), wcat.data_ptr(),
+                  _ptr(bcat), _stream(), cost=(4 * h * (kin + 2 * din), 0, ""))
+        ctx.shape, ctx.trans_inv, ctx.has_bias = (h, kin, din), trans_inv, b is not None
+        if bcat is None:
+            return wcat
+        return wcat, bcat
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dwcat, dbcat=None):
+        h, kin, din = ctx.shape
+        dwcat = dwcat.contiguous()
+        dw = torch.empty((h, kin), dtype=torch.float32, device=dwcat.device)
+        db = None
+        if ctx.has_bias and dbcat is not None:
+            dbcat = dbcat.contiguous()
+            db = torch.empty((h,), dtype=torch.float32, device=dwcat.device)
+        _abi.call("stinet_edgeconv_hoist_bwd", dwcat.data_ptr(), _ptr(dbcat) if db is not None else None, h, din,
+                  int(ctx.trans_inv), dw.data_ptr(), kin, _ptr(db), _stream(), cost=(4 * h * (kin + 2 * din), 0, ""))
+        return dw, db, None
+
+
+def edgeconv_hoist(w, b, trans_inv: bool):
+    """-> (Wcat [2H, din], bcat [2H] or None)"""
+    if b is None:
+        return EdgeConvHoistFn.apply(w, None, trans_inv), None
+    return EdgeConvHoistFn.apply(w, b, trans_inv)
+
+
 class AggregateFn(Function):
     """out[i] = reduce_{j->i} x[j]  (mean / add / max over in-edges)."""
 
@@ -295,23 +335,32 @@ class NormActResFn(Function):
         x = _mat(x)
         n, c = x.shape
         dev = x.device
-        mean = rstd = ws = None
-        nb = 0
+        mean = rstd = None
+        res = _mat(residual) if residual is not None else None
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+        nres = 1 if res is not None else 0
         if use_norm:
             assert seg is not None and seg.n_rows == n
             mean = torch.empty((seg.n_seg, c), dtype=torch.float32, device=dev)
             rstd = torch.empty((seg.n_seg, c), dtype=torch.float32, device=dev)
             nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
             ws = _ws(nb, dev)
-            _abi.call("stinet_segnorm_stats", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
-                      seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), _ptr(seg.gid), float(eps), mean.data_ptr(),
-                      rstd.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(8 * n * c, 3 * n * c, f"C{c}"))
-        res = _mat(residual) if residual is not None else None
-        out = torch.empty((n, c), dtype=torch.float32, device=dev)
-        gid = seg.gid if (use_norm and seg is not None) else None
-        _abi.call("stinet_segnorm_apply", x.data_ptr(), _ld(x), n, c, _ptr(gid), _ptr(mean), _ptr(rstd), _ptr(res),
-                  _ld(res) if res is not None else 0, act, out.data_ptr(), c, _stream(),
-                  cost=(4 * n * c * (3 if res is not None else 2), 4 * n * c, f"C{c}"))
+        if use_norm and seg.consistent:
+            # slices are the graphs: one entry point (a single cluster kernel when the slices are short)
+            _abi.call("stinet_segnorm_fwd", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
+                      seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), float(eps), _ptr(res),
+                      _ld(res) if res is not None else 0, act, out.data_ptr(), c, mean.data_ptr(), rstd.data_ptr(),
+                      ws.data_ptr(), nb, _stream(), cost=(4 * n * c * (3 + nres), 7 * n * c, f"C{c}"))
+        else:
+            if use_norm:
+                # the reference's linspace slices cut across graphs (ragged batch): sums by slice, lookups by graph id
+                _abi.call("stinet_segnorm_stats", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
+                          seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), _ptr(seg.gid), float(eps), mean.data_ptr(),
+                          rstd.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(8 * n * c, 3 * n * c, f"C{c}"))
+            gid = seg.gid if (use_norm and seg is not None) else None
+            _abi.call("stinet_segnorm_apply", x.data_ptr(), _ld(x), n, c, _ptr(gid), _ptr(mean), _ptr(rstd), _ptr(res),
+                      _ld(res) if res is not None else 0, act, out.data_ptr(), c, _stream(),
+                      cost=(4 * n * c * (2 + nres), 4 * n * c, f"C{c}"))
         ctx.save_for_backward(x, mean, rstd)
         ctx.seg, ctx.use_norm, ctx.act, ctx.has_res = seg, use_norm, act, residual is not None
         return out
@@ -334,9 +383,9 @@ class NormActResFn(Function):
                 nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
                 ws = _ws(nb, x.device)
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, seg.n_seg,
-                          seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), _ptr(seg.gid),
+                          seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), None,
                           mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, ws.data_ptr(), nb, _stream(),
-                          cost=(20 * n * c, 10 * n * c, f"C{c}"))
+                          cost=(16 * n * c, 10 * n * c, f"C{c}"))
             else:
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, 1, n, None,
                           None, None, None, None, ctx.act, dx.data_ptr(), c, None, 0, _stream())

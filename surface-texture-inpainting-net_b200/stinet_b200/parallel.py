@@ -46,6 +46,11 @@ class GradAllReducer:
         self._bucket_of = {}
         self._pending: List[int] = []
         self._handles = []
+        if self.world == 1:
+            # nothing to reduce: leave .grad unset so autograd hands each weight gradient over without the
+            # zero-fill + accumulate pass that pre-allocated bucket views cost (two launches per parameter)
+            self._sizes = []
+            return
         # reverse order: the last layers' gradients are produced first
         cur, cur_bytes = [], 0
         groups = []
@@ -72,6 +77,10 @@ class GradAllReducer:
                 p.register_post_accumulate_grad_hook(self._on_grad)
 
     def zero_grad(self):
+        if self.world == 1:
+            for p in self.params:
+                p.grad = None
+            return
         for flat in self.buckets:
             flat.zero_()
         self._pending = list(self._sizes)
