@@ -10,7 +10,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
 python __graft_entry__.py > $OUT/smoke_$TAG.log 2>&1; echo "smoke exit $?"; tail -1 $OUT/smoke_$TAG.log
 if [ "$MODE" = "tests" ]; then
-  ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_$TAG.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/pytest_$TAG.log
+  ( time timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ${PYTEST_EXTRA:-} ) > $OUT/pytest_$TAG.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/pytest_$TAG.log; grep -E "^(FAILED|ERROR)" $OUT/pytest_$TAG.log | head -40
 fi
 timeout 400 python bench.py --kernels-out $OUT/kernels_$TAG.json > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
 head -c 400 $OUT/bench_$TAG.json; echo

@@ -34,6 +34,11 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
 
 
+def _vec_ok(c: int, *tensors) -> bool:
+    """128-bit row access is possible: width, pitches and base addresses are multiples of four floats."""
+    return c % 4 == 0 and all(t is None or (t.data_ptr() % 16 == 0 and _ld(t) % 4 == 0) for t in tensors)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -345,7 +350,7 @@ class NormActResFn(Function):
             rstd = torch.empty((seg.n_seg, c), dtype=torch.float32, device=dev)
             nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
             ws = _ws(nb, dev)
-        if use_norm and seg.consistent:
+        if use_norm and seg.consistent and (seg.n_seg == 1 or _vec_ok(c, x, res)):
             # slices are the graphs: one entry point (a single cluster kernel when the slices are short)
             _abi.call("stinet_segnorm_fwd", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
                       seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), float(eps), _ptr(res),
@@ -353,7 +358,8 @@ class NormActResFn(Function):
                       ws.data_ptr(), nb, _stream(), cost=(4 * n * c * (3 + nres), 7 * n * c, f"C{c}"))
         else:
             if use_norm:
-                # the reference's linspace slices cut across graphs (ragged batch): sums by slice, lookups by graph id
+                # the reference's linspace slices cut across graphs (ragged batch), or rows of an odd width: sums by
+                # slice, lookups by graph id
                 _abi.call("stinet_segnorm_stats", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
                           seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), _ptr(seg.gid), float(eps), mean.data_ptr(),
                           rstd.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(8 * n * c, 3 * n * c, f"C{c}"))
@@ -383,7 +389,8 @@ class NormActResFn(Function):
                 nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
                 ws = _ws(nb, x.device)
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, seg.n_seg,
-                          seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), None,
+                          seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(),
+                          None if (seg.n_seg == 1 or _vec_ok(c, x, dout)) else _ptr(seg.gid),
                           mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, ws.data_ptr(), nb, _stream(),
                           cost=(16 * n * c, 10 * n * c, f"C{c}"))
             else:

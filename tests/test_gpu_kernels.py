@@ -136,7 +136,7 @@ def test_edge_conv_vs_literal_per_edge_mlp(kind, din, dout, trans_inv):
         assert float(out[(deg == 0).to(DEV)].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("c", [3, 64, 256])
+@pytest.mark.parametrize("c", [3, 8, 24, 64, 256, 1000])
 @pytest.mark.parametrize("pool", ["max", "mean"])
 def test_pool_unpool(c, pool):
     from stinet_b200 import ops, synthetic
@@ -178,6 +178,45 @@ def test_pool_unpool(c, pool):
     assert rel_err(xcd.grad, xcr.grad) <= TOL
 
 
+@pytest.mark.parametrize("c", [4, 20, 48, 128, 160])
+def test_pool_unpool_ragged_clusters(c):
+    """cluster sizes 0..9 in random order: every tail length of the four-at-a-time member loop, every team width."""
+    from stinet_b200 import ops
+    from stinet_b200.graph import ClusterCSR
+    g = torch.Generator().manual_seed(21)
+    sizes = torch.randint(0, 10, (301,), generator=g)
+    trace = torch.repeat_interleave(torch.arange(sizes.numel()), sizes)
+    trace = trace[torch.randperm(trace.numel(), generator=g)]
+    nf, nc = trace.numel(), sizes.numel()
+    x = torch.round(torch.randn(nf, c, generator=g) * 2) / 2
+    go = torch.randn(nc, c, generator=g)
+    cl = ClusterCSR(trace.to(DEV), nc)
+    for pool in ("max", "mean"):
+        xr = x.clone().requires_grad_(True)
+        if pool == "max":
+            ref, ref_arg = O.scatter_max(xr, trace, nc)
+        else:
+            ref = O.scatter_mean(xr, trace, nc)
+        ref.backward(go)
+        xd = x.to(DEV).requires_grad_(True)
+        if pool == "max":
+            out, arg = ops.pool_max(xd, cl)
+            assert torch.equal(arg.cpu().long(), ref_arg) and torch.equal(out.cpu(), ref.detach())
+        else:
+            out = ops.pool_mean(xd, cl)
+        out.backward(go.to(DEV))
+        assert rel_err(out, ref) <= TOL and rel_err(xd.grad, xr.grad) <= TOL
+    xc = torch.randn(nc, c, generator=g)
+    gf = torch.randn(nf, c, generator=g)
+    xcr = xc.clone().requires_grad_(True)
+    xcr[trace].backward(gf)
+    xcd = xc.to(DEV).requires_grad_(True)
+    up = ops.unpool(xcd, cl)
+    up.backward(gf.to(DEV))
+    assert torch.equal(up.cpu(), xc[trace])
+    assert rel_err(xcd.grad, xcr.grad) <= TOL
+
+
 def test_graph_id_pooling_int():
     from stinet_b200 import synthetic
     from stinet_b200.graph import GraphCache
@@ -190,13 +229,17 @@ def test_graph_id_pooling_int():
     cache.check_status()
 
 
-@pytest.mark.parametrize("c", [3, 64, 192])
-@pytest.mark.parametrize("layout", ["single", "equal", "ragged"])
+# layouts cover every instance-norm path: one cluster kernel with rows in registers (single / equal / empty_slice),
+# cluster kernel re-reading rows (equal_mid: 8 CTAs x 375 rows), long slices (stats + slice apply: single_long,
+# equal_long), graph-id lookups (ragged, and odd widths with several graphs)
+@pytest.mark.parametrize("c", [3, 40, 64, 192])
+@pytest.mark.parametrize("layout", ["single", "equal", "ragged", "equal_mid", "single_long", "equal_long"])
 def test_instance_norm_elu_residual(c, layout):
     from stinet_b200.models.modules import FastInstanceNorm
     from stinet_b200._abi import ACT_ELU, StinetError
     g = torch.Generator().manual_seed(5)
-    counts = {"single": [700], "equal": [300, 300, 300], "ragged": [500, 77, 323]}[layout]
+    counts = {"single": [700], "equal": [300, 300, 300], "ragged": [500, 77, 323], "equal_mid": [3000, 3000],
+              "single_long": [17001], "equal_long": [16500, 16500]}[layout]
     n = sum(counts)
     x = torch.randn(n, c, generator=g) * 3 + 1.5
     res = torch.randn(n, c, generator=g)
@@ -216,6 +259,14 @@ def test_instance_norm_elu_residual(c, layout):
     out.backward(go.to(DEV))
     assert rel_err(xd.grad, xr.grad) <= TOL
     assert torch.equal(rd.grad.cpu(), go)
+    # no residual, no activation (the plain module call of the reference)
+    x2 = x.to(DEV).requires_grad_(True)
+    out2 = norm(x2, None if batch is None else batch.to(DEV))
+    xr2 = x.clone().requires_grad_(True)
+    ref2 = O.fast_instance_norm(xr2, batch)
+    ref2.backward(go)
+    out2.backward(go.to(DEV))
+    assert rel_err(out2, ref2) <= TOL and rel_err(x2.grad, xr2.grad) <= TOL
 
 
 @pytest.mark.parametrize("m,n,k", [(1000, 16, 10), (777, 128, 64), (130, 3, 64), (4097, 256, 20), (64, 512, 256), (5, 8, 4)])
