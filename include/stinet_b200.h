@@ -185,6 +185,26 @@ int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t ld
                         int64_t ldw, float* dbias, int64_t M, int64_t N, int64_t K, int precision, void* workspace,
                         size_t workspace_bytes, stinet_stream_t stream);
 
+/* ---- per-step graph metrics (replace utils/metrics/graph_metrics.py:6-72 as called from
+ * trainers/inpainting3d_trainer.py:254-263) on the level-0 CSR by target.  Scalar results are written to `out` on the
+ * device (float[1], psnr float[2] = {score, rows used}); reductions are deterministic (double partials, fixed order).
+ *   laplace            out[i,c] = sum_{j->i} x[j,c] - deg_i x[i,c]                     (GraphLaplaceOperator.forward :10-13)
+ *   laplace_variance   biased variance over vertices of laplace(0.299 r + 0.587 g + 0.114 b)   (GraphLaplaceVariance :24-30)
+ *   total_variation    sum_edges sum_c |x[src,c] - x[dst,c]| / (n * channels)            (:33-37)
+ *   psnr               -10 log10(mean(((x - y) / data_range)^2) + 1e-8) over rows with mask > 0 (mask NULL: all rows),
+ *                      i.e. psnr(x[mask > 0], y[mask > 0]) without the boolean-index copies (:40-72) */
+size_t stinet_metrics_workspace_bytes(int64_t n);
+int stinet_graph_laplace(const float* x, int64_t ldx, const int32_t* rowptr_t, const int32_t* col_t, int64_t n,
+                         int64_t channels, float* out, int64_t ldo, stinet_stream_t stream);
+int stinet_graph_laplace_variance(const float* x, int64_t ldx, const int32_t* rowptr_t, const int32_t* col_t, int64_t n,
+                                  float* out, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+int stinet_graph_total_variation(const float* x, int64_t ldx, const int32_t* rowptr_t, const int32_t* col_t, int64_t n,
+                                 int64_t channels, float* out, void* workspace, size_t workspace_bytes,
+                                 stinet_stream_t stream);
+int stinet_psnr(const float* x, int64_t ldx, const float* y, int64_t ldy, const float* mask, int64_t n,
+                int64_t channels, float data_range, float* out, void* workspace, size_t workspace_bytes,
+                stinet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -434,3 +434,23 @@ def graph_laplace_variance(x: torch.Tensor, edge_index: torch.Tensor) -> torch.T
 def graph_total_variation(x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
     h, w = x.shape
     return torch.abs(x[edge_index[0]] - x[edge_index[1]]).sum() / (h * w)
+
+
+def graph_laplace(x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """GraphLaplaceOperator.forward (utils/metrics/graph_metrics.py:10-16): add-aggregate [1 | x_j], then
+    sum_j x_j - deg_i x_i."""
+    xi = torch.cat([x.new_ones(x.shape[0], 1), x], dim=1)
+    prop = scatter_add(xi.index_select(0, edge_index[0]), edge_index[1], x.size(0))
+    return prop[:, 1:] - prop[:, 0:1] * x
+
+
+def psnr(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/metrics/graph_metrics.py:40-72 with convert_to_greyscale=False; `mask` restates the trainer's
+    boolean-indexed call (trainers/inpainting3d_trainer.py:261-263)."""
+    if mask is not None:
+        sel = mask.reshape(-1) > 0
+        x, y = x[sel], y[sel]
+    x = x / data_range
+    y = y / data_range
+    mse = torch.mean((x - y) ** 2, dim=[0, 1])
+    return -10 * torch.log10(mse + 1e-8)

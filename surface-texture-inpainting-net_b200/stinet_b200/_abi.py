@@ -41,6 +41,11 @@ SIGNATURES = {
     "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, SZ, P]),
     "stinet_segnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, I64, P]),
     "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, SZ, P]),
+    "stinet_metrics_workspace_bytes": (SZ, [I64]),
+    "stinet_graph_laplace": (I, [P, I64, P, P, I64, I64, P, I64, P]),
+    "stinet_graph_laplace_variance": (I, [P, I64, P, P, I64, P, P, SZ, P]),
+    "stinet_graph_total_variation": (I, [P, I64, P, P, I64, I64, P, P, SZ, P]),
+    "stinet_psnr": (I, [P, I64, P, I64, P, I64, I64, F, P, P, SZ, P]),
     "stinet_gemm_workspace_bytes": (SZ, [I64, I64, I64, I]),
     "stinet_linear_fwd": (I, [P, I64, P, I64, P, P, P, I64, I64, I64, I64, I, P, SZ, P]),
     "stinet_linear_dgrad": (I, [P, I64, P, I64, P, I64, I64, I64, I64, I, P, SZ, P]),
