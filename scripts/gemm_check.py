@@ -17,6 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "surface-texture-inpainting-net_b200"))
 SHAPES = [  # (M, N, K)
     (300, 128, 64), (1000, 192, 96), (129, 64, 32), (5136, 512, 1024),
     (327696, 256, 64), (327696, 64, 128), (81936, 512, 128), (1296, 4096, 1024), (1296, 1024, 2048),
+    (5136, 2048, 512), (5136, 512, 1024), (20496, 1024, 256), (20496, 256, 512), (1296, 1024, 512), (81936, 128, 256),
 ]
 
 

@@ -11,7 +11,7 @@ names = ["producer<-empty", "split<-full", "mma<-operands", "mma<-tmem_empty", "
 dev = torch.device("cuda", 0); st = torch.cuda.current_stream().cuda_stream
 for prec in sys.argv[1:] or ["fp32", "tf32"]:
     p = PREC[prec]
-    for (M, N, K) in [(327696, 256, 64), (327696, 64, 128), (81936, 512, 128), (1296, 4096, 1024), (5136, 512, 1024)]:
+    for (M, N, K) in [(327696, 256, 64), (327696, 64, 128), (81936, 512, 128), (1296, 4096, 1024), (1296, 1024, 2048), (5136, 512, 1024)]:
         x = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev); y = torch.empty(M, N, device=dev)
         nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, p); ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
         for _ in range(3):

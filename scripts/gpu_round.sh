@@ -14,7 +14,7 @@ if [ "$MODE" = "tests" ]; then
 fi
 timeout 400 python bench.py --kernels-out $OUT/kernels_$TAG.json > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
 head -c 400 $OUT/bench_$TAG.json; echo
-timeout 300 python bench.py --dtype bf16 --no-cpu-baseline --kernels-out $OUT/kernels_bf16_$TAG.json > $OUT/bench_bf16_$TAG.json 2>> $OUT/bench_$TAG.err; echo "bench bf16 exit $?"
+[ -n "$SKIP_BF16" ] || timeout 300 python bench.py --dtype bf16 --no-cpu-baseline --kernels-out $OUT/kernels_bf16_$TAG.json > $OUT/bench_bf16_$TAG.json 2>> $OUT/bench_$TAG.err; echo "bench bf16 exit $?"
 head -c 400 $OUT/bench_bf16_$TAG.json; echo
 if [ "$MODE" = "tests" ]; then
   timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err; echo "ref exit $?"
@@ -27,11 +27,11 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 # full capture of the dominant kernels, eager launches: pass 1 = start of forward (level 0/1 shapes), pass 2 = start of
 # backward (output blocks on level 0 come first)
 timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:'edge_message_fwd|pool_max_fwd|seg_colreduce|segnorm_apply|gemm_tc' -c 14 \
+  -k regex:'edge_message_fwd|pool_max_fwd|seg_colreduce|segnorm_apply|segnorm_fused_fwd|segnorm_slice_apply|row_gather|gemm_tc' -c ${NCU_COUNT:-24} \
   -o $OUT/prof_fwd_$TAG -f python bench.py --steps 1 --warmup 3 --no-e2e --no-profile --no-cpu-baseline --no-graph \
   --profiler-range > $OUT/ncu_full_fwd_$TAG.log 2>&1; echo "ncu full fwd exit $?"
 timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  --kernel-name-base demangled -k regex:"bwd|colsum_partial|gemm_tc_kernel<128, 0, 1|gemm_tc_kernel<128, 1, 1" -c 14 \
+  --kernel-name-base demangled -k regex:"bwd|colsum_partial|cluster_sum|gemm_tc_kernel<128, 0, 1|gemm_tc_kernel<128, 1, 1" -c ${NCU_COUNT:-24} \
   -o $OUT/prof_bwd_$TAG -f python bench.py --steps 1 --warmup 3 --no-e2e --no-profile --no-cpu-baseline --no-graph \
   --profiler-range > $OUT/ncu_full_bwd_$TAG.log 2>&1; echo "ncu full bwd exit $?"
 for f in fwd bwd; do

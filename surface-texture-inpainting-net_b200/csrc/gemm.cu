@@ -6,6 +6,7 @@
 // Fallback for operands TMA cannot address (row pitch not a multiple of 16 B: the 10-channel input, the 3-channel
 // head): 128x64x16 FFMA tiles, 256 threads, 8x4 outputs per thread, register-staged double buffering.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -273,6 +274,26 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// fp32 -> (hi, lo) TF32 planes for the pre-split 3xTF32 GEMM: hi = x rounded to TF32 (10 explicit significand bits,
+// the same integer rounding the in-kernel split uses), lo = x - hi (exact in fp32).  Packed planes, pitch = cols.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
+                                                         float* __restrict__ hi, float* __restrict__ lo) {
+  const int cpr = cols >> 2;
+  const int64_t total = rows * cpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / cpr;
+    const int c = (int)(idx % cpr) << 2;
+    const float4 v = ld_stream(reinterpret_cast<const float4*>(x + r * ldx + c));
+    float4 h, l;
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + r * cols + c) = h;
+    *reinterpret_cast<float4*>(lo + r * cols + c) = l;
+  }
+}
+
 static int pick_splits(int64_t I, int64_t J, int64_t T) {
   int64_t tiles = ceil_div(I, BM) * ceil_div(J, BN);
   int64_t want = ceil_div(2 * kSMs, tiles);
@@ -317,7 +338,19 @@ static int tc_mode(int precision) {
 static bool valid_precision(int p) { return p >= STINET_PREC_FP32 && p <= STINET_PREC_BF16X3; }
 static bool is_bf16_mode(int mode) { return mode == tc::MODE_BF16 || mode == tc::MODE_BF16X3; }
 
+// fp32 mode, C[I,J] over T: split the operands in HBM first (MODE_TF32X3P) when the GEMM is compute-heavy enough that
+// the in-kernel split (shared-memory bandwidth) is the limiter and the two extra HBM passes are cheap next to it:
+// flops per operand byte = I*J / (2*(I+J)) above a threshold (STINET_TC_PRESPLIT overrides it; 0 disables).
+static bool tc_presplit(int precision, int64_t I, int64_t J, int64_t T) {
+  static const int thr = [] { const char* e = getenv("STINET_TC_PRESPLIT"); return e ? atoi(e) : 160; }();
+  if (precision != STINET_PREC_FP32 || thr <= 0) return false;
+  if ((I | J | T) & 3) return false;                       // packed planes must keep 16-byte row pitches
+  return I * J >= (int64_t)thr * 2 * (I + J) && T >= 256;
+}
+
 struct GemmWs {
+  float *a32, *w32, *c32;                  // fp32 pre-split mode: hi planes of A [M,K], W [N,K], dC [M,N] ...
+  float *a32lo, *w32lo, *c32lo;            // ... and their lo planes (nullptr when no entry point of this shape pre-splits)
   float *splitk, *colsum;
   __nv_bfloat16 *a16, *w16, *c16;          // bf16 copies of A [M,K], W [N,K], dC [M,N]
   __nv_bfloat16 *a16lo, *w16lo, *c16lo;    // bf16x3 mode: the residual planes (nullptr otherwise)
@@ -351,6 +384,17 @@ static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K, int precis
   w.w16lo = x3 ? reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16 + w1) : nullptr;
   w.c16lo = x3 ? reinterpret_cast<__nv_bfloat16*>(p + sk + cs + a16 + w16 + c1) : nullptr;
   w.bytes = sk + cs + a16 + w16 + c16;
+  // fp32 pre-split planes (any of fwd / dgrad / wgrad of this shape may ask for them)
+  w.a32 = w.w32 = w.c32 = w.a32lo = w.w32lo = w.c32lo = nullptr;
+  if (M > 0 && (tc_presplit(precision, rows, N, K) || tc_presplit(precision, rows, K, N) || tc_presplit(precision, N, K, rows))) {
+    const size_t pa = up(4 * (size_t)rows * K), pw = up(4 * (size_t)N * K), pc = up(4 * (size_t)rows * N);
+    char* q = p + w.bytes;
+    w.a32 = reinterpret_cast<float*>(q);            w.a32lo = reinterpret_cast<float*>(q + pa);
+    w.w32 = reinterpret_cast<float*>(q + 2 * pa);   w.w32lo = reinterpret_cast<float*>(q + 2 * pa + pw);
+    w.c32 = reinterpret_cast<float*>(q + 2 * pa + 2 * pw);
+    w.c32lo = reinterpret_cast<float*>(q + 2 * pa + 2 * pw + pc);
+    w.bytes += 2 * (pa + pw + pc);
+  }
   return w;
 }
 
@@ -360,6 +404,12 @@ static void cast_bf16(const float* x, int64_t ld, int64_t rows, int64_t cols, __
                       cudaStream_t s) {
   K(cast_bf16_kernel<<<wave_grid(rows * (cols / 8), 256, 8), 256, 0, s>>>(x, ld, rows, (int)cols, y, cols, lo));
 }
+
+static void split_tf32(const float* x, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo, cudaStream_t s) {
+  K(split_tf32_kernel<<<wave_grid(rows * (cols / 4), 256, 8), 256, 0, s>>>(x, ld, rows, (int)cols, hi, lo));
+}
+// fp32 matrix the split kernel can read with 16-byte accesses
+static bool splittable(const float* x, int64_t ld, int64_t cols) { return aligned16(x) && ld % 4 == 0 && cols % 4 == 0; }
 
 }  // namespace stinet
 
@@ -391,6 +441,14 @@ extern "C" int stinet_linear_fwd(const float* A, int64_t lda, const float* W, in
         cast_bf16(A, lda, M, K, w.a16, w.a16lo, s);
         cast_bf16(W, ldw, N, K, w.w16, w.w16lo, s);
         p.A = w.a16; p.lda = K; p.B = w.w16; p.ldb = K; p.A_lo = w.a16lo; p.B_lo = w.w16lo;
+      }
+    } else if (tc_presplit(precision, M, N, K) && splittable(A, lda, K) && splittable(W, ldw, K)) {
+      GemmWs w = carve_gemm(workspace, M, N, K, precision);
+      if (workspace && workspace_bytes >= w.bytes && w.a32) {
+        split_tf32(A, lda, M, K, w.a32, w.a32lo, s);
+        split_tf32(W, ldw, N, K, w.w32, w.w32lo, s);
+        p.A = w.a32; p.lda = K; p.B = w.w32; p.ldb = K; p.A_lo = w.a32lo; p.B_lo = w.w32lo;
+        p.mode = tc::MODE_TF32X3P;
       }
     }
     if (ok && tc::eligible(p)) {
@@ -438,6 +496,14 @@ extern "C" int stinet_linear_dgrad(const float* dC, int64_t ldc, const float* W,
         cast_bf16(dC, ldc, M, N, w.c16, w.c16lo, s);
         cast_bf16(W, ldw, N, K, w.w16, w.w16lo, s);
         p.A = w.c16; p.lda = N; p.B = w.w16; p.ldb = K; p.A_lo = w.c16lo; p.B_lo = w.w16lo;
+      }
+    } else if (tc_presplit(precision, M, K, N) && splittable(dC, ldc, N) && splittable(W, ldw, K)) {
+      GemmWs w = carve_gemm(workspace, M, N, K, precision);
+      if (workspace && workspace_bytes >= w.bytes && w.c32) {
+        split_tf32(dC, ldc, M, N, w.c32, w.c32lo, s);
+        split_tf32(W, ldw, N, K, w.w32, w.w32lo, s);
+        p.A = w.c32; p.lda = N; p.B = w.w32; p.ldb = K; p.A_lo = w.c32lo; p.B_lo = w.w32lo;
+        p.mode = tc::MODE_TF32X3P;
       }
     }
     if (ok && tc::eligible(p)) {
@@ -487,6 +553,11 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
         cast_bf16(A, lda, M, K, w.a16, w.a16lo, s);
         p.A = w.c16; p.lda = N; p.B = w.a16; p.ldb = K; p.A_lo = w.c16lo; p.B_lo = w.a16lo;
       }
+    } else if (tc_presplit(precision, N, K, M) && w.c32 && splittable(dC, ldc, N) && splittable(A, lda, K)) {
+      split_tf32(dC, ldc, M, N, w.c32, w.c32lo, s);
+      split_tf32(A, lda, M, K, w.a32, w.a32lo, s);
+      p.A = w.c32; p.lda = N; p.B = w.a32; p.ldb = K; p.A_lo = w.c32lo; p.B_lo = w.a32lo;
+      p.mode = tc::MODE_TF32X3P;
     }
     if (ok && tc::eligible(p)) {
       int rc = tc::run(p, s);

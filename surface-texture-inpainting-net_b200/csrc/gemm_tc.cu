@@ -21,6 +21,9 @@
 //            error ~2^-22 per product, i.e. fp32-class, which the 1e-5 parity bar against the reference needs;
 //   TF32X1 : fp32 storage, one kind::tf32 pass (operands truncated by the tensor core);
 //   BF16   : bf16 storage (the caller casts), kind::f16 with fp32 accumulation -- 2e-2 per operator;
+//   TF32X3P: as TF32X3, but the caller hands over the hi / lo planes (fp32 storage, split once in HBM): no in-smem
+//            split, which costs 96 KB of shared-memory traffic per k-block next to the 96 KB the three MMAs read --
+//            the kernel is shared-memory-bandwidth bound, so compute-heavy shapes run ~1.4x faster pre-split;
 //   BF16X3 : the caller splits every fp32 operand into two bf16 planes x = hi + lo in HBM; TMA loads all four tiles
 //            and the products are evaluated as  hi*hi + hi*lo + lo*hi  on kind::f16 (error ~2^-16 per product) --
 //            the mode that keeps a whole deep network within 2e-2 while running bf16 tiles only.
@@ -124,6 +127,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// smem -> global tile store through the tensor map (coordinates: column, row, split plane); rows / columns outside the
+// tensor are clipped by the TMA unit.  bulk_group completion: wait_read = the smem source may be overwritten,
+// wait_all = the global writes are done.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -191,7 +207,8 @@ template <int BN, int MODE>
 struct Cfg {
   static constexpr bool kBf16 = MODE == MODE_BF16 || MODE == MODE_BF16X3;
   static constexpr bool kConv = MODE == MODE_TF32X3;               // operand split done in smem by the split warps
-  static constexpr bool kPre = MODE == MODE_BF16X3;                // operand split done by the caller in HBM
+  static constexpr bool kPre = MODE == MODE_BF16X3 || MODE == MODE_TF32X3P;  // operand split done by the caller in HBM
+  static constexpr bool kFp32 = MODE == MODE_TF32X3 || MODE == MODE_TF32X3P;   // fp32-class result: promotion + correction accumulator
   static constexpr bool kSplit = kConv || kPre;                    // stage holds hi and lo tiles, three MMAs per k-step
   static constexpr int kElemBytes = kBf16 ? 2 : 4;
   static constexpr int BKE = kRowBytes / kElemBytes;  // reduction elements per stage: 32 fp32 / 64 bf16
@@ -205,7 +222,7 @@ struct Cfg {
   static constexpr int kStagesRaw = (227 * 1024 - 1024 - (int)kStagingBytes - (int)kBarBytes) / (int)kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   // two accumulator buffers of BN columns; fp32 mode doubles that for the separate correction-term accumulators
-  static constexpr uint32_t kTmemCols = (kConv ? 4 : 2) * BN;
+  static constexpr uint32_t kTmemCols = (kFp32 ? 4 : 2) * BN;
   static constexpr int kEpiCols = BN / 2;             // accumulator columns owned by one epilogue warp
   // fp32 mode: the tensor core adds into its fp32 accumulator with truncation, so the error of a long reduction
   // grows linearly with K (measured: ~5e-9 * K relative).  Every kPromote k-blocks (128 reduction elements) the
@@ -216,7 +233,8 @@ struct Cfg {
 template <int BN, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcArgs g) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmC, TcArgs g) {
   using C_ = Cfg<BN, MODE>;
   constexpr bool kBf16 = C_::kBf16;
   constexpr int kStages = C_::kStages;
@@ -239,6 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     if (C_::kPre) {
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
@@ -443,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cc = 0; cc < EC; cc += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + cc, r);
-          if (C_::kConv && g.split_acc) {
+          if (C_::kFp32 && g.split_acc) {
             uint32_t r2[32];
             tmem_ld32(taddr + 2 * BN + cc, r2);
 #pragma unroll
@@ -462,37 +481,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) mbar_arrive(tempty_bar(buf));
         ++acc_it;
       }
-      // ---- write the tile out
+      // ---- write the tile out: (+bias) -> this warp's swizzled 32x32 staging block -> one TMA store per block
       DBG_T0();
-      const int row = w.i0 + q * 32 + lane;                // the row this thread holds
+      const int row0 = w.i0 + q * 32;                      // first row of this warp's lane quarter
+      const int row = row0 + lane;                         // the row this thread holds
       const bool add_bias = g.bias != nullptr && row < g.I && (g.rowmask == nullptr || g.rowmask[row] > 0);
-      float* cbase = g.C + (int64_t)w.z * g.I * g.ldc;
+      if (row0 < g.I) {
 #pragma unroll
-      for (int cc = 0; cc < EC; cc += 32) {
-        const int jb = w.j0 + h * EC + cc;                 // first global column of this 32-column block
+        for (int cc = 0; cc < EC; cc += 32) {
+          const int jb = w.j0 + h * EC + cc;               // first global column of this 32-column block
+          if (jb >= g.J) break;
+          if (lane == 0) bulk_wait_read();                 // the previous block has left the staging buffer
+          __syncwarp();
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 v = make_float4(acc[cc + 4 * c4], acc[cc + 4 * c4 + 1], acc[cc + 4 * c4 + 2], acc[cc + 4 * c4 + 3]);
-          if (add_bias && jb + 4 * c4 < g.J) {
-            const float4 b = *reinterpret_cast<const float4*>(g.bias + jb + 4 * c4);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 v = make_float4(acc[cc + 4 * c4], acc[cc + 4 * c4 + 1], acc[cc + 4 * c4 + 2], acc[cc + 4 * c4 + 3]);
+            if (add_bias && jb + 4 * c4 < g.J) {
+              const float4 b = *reinterpret_cast<const float4*>(g.bias + jb + 4 * c4);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            stage[lane * 8 + (c4 ^ (lane & 7))] = v;       // the 128-byte swizzle of the tensor map, by hand
           }
-          stage[lane * 8 + (c4 ^ (lane & 7))] = v;
+          fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0) tma_store_3d(&tmC, smem_u32(stage), jb, row0, w.z);
         }
-        __syncwarp();
-        const int c4r = lane & 7;
-        const int gcol = jb + 4 * c4r;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          const float4 v = stage[rr * 8 + (c4r ^ (rr & 7))];
-          const int grow = w.i0 + q * 32 + rr;
-          if (grow < g.I && gcol < g.J) *reinterpret_cast<float4*>(cbase + (int64_t)grow * g.ldc + gcol) = v;
-        }
-        __syncwarp();
       }
       DBG_ADD(5);
     }
+    if (lane == 0) bulk_wait_all();
     DBG_FLUSH(threadIdx.x == 32 * kEpiWarp0, 4, 5);
   }
   tcgen05_fence_before();
@@ -556,13 +573,29 @@ static int launch(const Problem& p, cudaStream_t s) {
   if (rc) return rc;
   CUtensorMap tmA2 = tmA, tmB2 = tmB;
   if (C_::kPre) {
-    STINET_REQUIRE(p.A_lo && p.B_lo, STINET_ERR_ARG, "gemm_tc: bf16x3 needs the lo planes of both operands");
-    if (!A_MN) rc = make_map(&tmA2, p.A_lo, p.T, p.I, p.lda, true, C_::BKE, BM, CU_TENSOR_MAP_SWIZZLE_128B);
-    else rc = make_map(&tmA2, p.A_lo, p.I, p.T, p.lda, true, C_::MNE, C_::BKE, CU_TENSOR_MAP_SWIZZLE_128B);
+    // the lo planes have the element type, pitch and layout of the hi planes
+    STINET_REQUIRE(p.A_lo && p.B_lo, STINET_ERR_ARG, "gemm_tc: a pre-split mode needs the lo planes of both operands");
+    const CUtensorMapSwizzle mn_swz = bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (!A_MN) rc = make_map(&tmA2, p.A_lo, p.T, p.I, p.lda, bf16, C_::BKE, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_map(&tmA2, p.A_lo, p.I, p.T, p.lda, bf16, C_::MNE, C_::BKE, mn_swz);
     if (rc) return rc;
-    if (!B_MN) rc = make_map(&tmB2, p.B_lo, p.T, p.J, p.ldb, true, C_::BKE, BN, CU_TENSOR_MAP_SWIZZLE_128B);
-    else rc = make_map(&tmB2, p.B_lo, p.J, p.T, p.ldb, true, C_::MNE, C_::BKE, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!B_MN) rc = make_map(&tmB2, p.B_lo, p.T, p.J, p.ldb, bf16, C_::BKE, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_map(&tmB2, p.B_lo, p.J, p.T, p.ldb, bf16, C_::MNE, C_::BKE, mn_swz);
     if (rc) return rc;
+  }
+  // output (or split-K partial planes [splits, I, J]) as a 3-D tensor: 32 x 32 fp32 boxes, 128-byte swizzle
+  CUtensorMap tmC;
+  {
+    EncodeTiledFn fn = encode_fn();
+    STINET_REQUIRE(fn != nullptr, STINET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {(cuuint64_t)p.J, (cuuint64_t)p.I, (cuuint64_t)p.splits};
+    cuuint64_t strides[2] = {(cuuint64_t)p.ldc * 4, (cuuint64_t)p.I * (cuuint64_t)p.ldc * 4};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    STINET_REQUIRE(r == CUDA_SUCCESS, STINET_ERR_CUDA, "cuTensorMapEncodeTiled (C) failed (%d): I %lld J %lld ldc %lld",
+                   (int)r, (long long)p.I, (long long)p.J, (long long)p.ldc);
   }
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE>;
   static bool attr_set = false;  // per instantiation; idempotent, so a race only repeats the call
@@ -582,9 +615,9 @@ static int launch(const Problem& p, cudaStream_t s) {
   static const int env_split = [] { const char* e = getenv("STINET_TC_SPLITACC"); return e ? atoi(e) : 1; }();
   TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split,
            tiles_j, tiles_i * tiles_j, (int)units,
-           C_::kConv ? (env_promote > 0 ? env_promote : 4) : (1 << 28), C_::kConv ? env_split : 0};
+           C_::kFp32 ? (env_promote > 0 ? env_promote : 4) : (1 << 28), C_::kFp32 ? env_split : 0};
   const unsigned grid = (unsigned)(units < kSMs ? units : kSMs);   // persistent: one CTA per SM walks the work units
-  K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, g));
+  K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, tmC, g));
   return check_launch("gemm_tc");
 }
 
@@ -608,7 +641,8 @@ bool eligible(const Problem& p) {
   const int64_t align_elems = 16 / esz;
   if (p.I <= 0 || p.J <= 0 || p.T <= 0) return false;
   if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
-  if (p.mode == MODE_BF16X3 && (!p.A_lo || !p.B_lo || !aligned16(p.A_lo) || !aligned16(p.B_lo))) return false;
+  if ((p.mode == MODE_BF16X3 || p.mode == MODE_TF32X3P) &&
+      (!p.A_lo || !p.B_lo || !aligned16(p.A_lo) || !aligned16(p.B_lo))) return false;
   if (p.lda % align_elems || p.ldb % align_elems) return false;
   if (p.ldc % 4 || p.J % 4) return false;
   if (p.bias && !aligned16(p.bias)) return false;
@@ -624,6 +658,7 @@ int run(const Problem& p, cudaStream_t s) {
     case MODE_TF32X1: return launch_major<MODE_TF32X1>(p, s);
     case MODE_BF16: return launch_major<MODE_BF16>(p, s);
     case MODE_BF16X3: return launch_major<MODE_BF16X3>(p, s);
+    case MODE_TF32X3P: return launch_major<MODE_TF32X3P>(p, s);
   }
   set_error("gemm_tc: unknown mode %d", p.mode);
   return STINET_ERR_ARG;

@@ -6,11 +6,12 @@
 namespace stinet {
 namespace tc {
 
-enum { MODE_TF32X3 = 0, MODE_TF32X1 = 1, MODE_BF16 = 2, MODE_BF16X3 = 3 };
+enum { MODE_TF32X3 = 0, MODE_TF32X1 = 1, MODE_BF16 = 2, MODE_BF16X3 = 3, MODE_TF32X3P = 4 };
 
 // C[i,j] = sum_t A'(i,t) B'(t,j);  a_mn: A'(i,t) = A[t*lda + i] (else A[i*lda + t]); same for B with j.
 // A and B are fp32 (TF32 modes) or bf16 (MODE_BF16, MODE_BF16X3); C is fp32.  MODE_BF16X3: every operand is given as
 // two bf16 planes, x = hi + lo (A/B = hi, A_lo/B_lo = lo, same pitch), and the kernel evaluates hi*hi + hi*lo + lo*hi.
+// MODE_TF32X3P: the same with two fp32 planes (hi = x rounded to TF32, lo = x - hi).
 // With splits > 1, split z covers t in [z*t_per_split, (z+1)*t_per_split) and writes its partial to C + z*I*ldc.
 struct Problem {
   const void* A; int64_t lda; bool a_mn;

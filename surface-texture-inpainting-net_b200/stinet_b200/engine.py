@@ -50,7 +50,22 @@ def batch_signature(batch) -> tuple:
 
 
 class _Captured:
-    __slots__ = ("static", "graph_a", "graph_b", "loss", "launches")
+    __slots__ = ("static", "graph_a", "graph_b", "loss", "launches", "flat", "views", "staging", "staged", "ready", "free")
+
+
+def _flat_views(items, device):
+    """One flat device buffer holding every tensor of a batch (256-byte aligned views), so that the whole batch moves
+    device-to-device with a single copy."""
+    layout, off = [], 0
+    for k, v in items:
+        nbytes = v.numel() * v.element_size()
+        layout.append((k, off, nbytes, v.dtype, tuple(v.shape)))
+        off += (nbytes + 255) & ~255
+    flat = torch.empty(max(off, 256), dtype=torch.uint8, device=device)
+
+    def views(buf):
+        return {k: buf[o:o + n].view(dt).view(shape) for k, o, n, dt, shape in layout}
+    return flat, views
 
 
 class GraphedTrainStep:
@@ -66,6 +81,7 @@ class GraphedTrainStep:
         self._cache: Dict[tuple, _Captured] = {}
         self.captures = 0
         self.replayed_launches = 0      # library kernels executed through graph replays (bench.py `gpu_launches`)
+        self._copy_stream = None
 
     # ---- pieces of one step (run eagerly for warm-up, then under capture) -------------------------------------
     def _fwd_bwd(self, static):
@@ -88,9 +104,12 @@ class GraphedTrainStep:
         dev = next(self.net.parameters()).device
         c = _Captured()
         c.static = GraphBatch()
-        for k, v in _tensor_items(batch):
-            c.static.__dict__[k] = v.to(dev, non_blocking=True).clone()
+        c.flat, c.views = _flat_views(list(_tensor_items(batch)), dev)      # static inputs of the graph: views of one buffer
+        for k, v in c.views(c.flat).items():
+            v.copy_(batch[k], non_blocking=True)
+            c.static.__dict__[k] = v
         c.static.__dict__["_nv_host"] = sig[1]
+        c.staging = c.staged = c.ready = c.free = None
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -124,6 +143,29 @@ class GraphedTrainStep:
         self.captures += 1
         return c
 
+    def prefetch(self, batch) -> bool:
+        """Start moving the NEXT batch (pinned host memory) to the device on a copy stream while the current step is
+        still running; the following `step(batch)` call with the same object then only pays one device-to-device copy.
+        What a DataLoader with pin_memory + a prefetching collate thread gives the reference trainer.  Returns False
+        (and does nothing) for a batch shape that has not been captured yet."""
+        c = self._cache.get(batch_signature(batch))
+        if c is None:
+            return False
+        dev = c.flat.device
+        if c.staging is None:
+            c.staging = torch.empty_like(c.flat)
+            c.ready, c.free = torch.cuda.Event(), torch.cuda.Event()
+            c.free.record(torch.cuda.current_stream(dev))
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        self._copy_stream.wait_event(c.free)             # the previous staged batch has been consumed
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in c.views(c.staging).items():
+                v.copy_(batch[k], non_blocking=True)
+            c.ready.record(self._copy_stream)
+        c.staged = batch
+        return True
+
     def __call__(self, batch) -> torch.Tensor:
         sig = batch_signature(batch)
         c = self._cache.get(sig)
@@ -131,8 +173,15 @@ class GraphedTrainStep:
             if len(self._cache) >= self.max_cached:
                 self._cache.pop(next(iter(self._cache)))
             c = self._cache[sig] = self._capture(batch, sig)
-        for k, v in _tensor_items(batch):
-            c.static.__dict__[k].copy_(v, non_blocking=True)
+        if c.staged is batch:                            # prefetched: wait for the copy stream, one D2D copy
+            cur = torch.cuda.current_stream(c.flat.device)
+            cur.wait_event(c.ready)
+            c.flat.copy_(c.staging, non_blocking=True)
+            c.free.record(cur)
+            c.staged = None
+        else:
+            for k, v in _tensor_items(batch):
+                c.static.__dict__[k].copy_(v, non_blocking=True)
         c.graph_a.replay()
         self.replayed_launches += c.launches
         if c.graph_b is not None:

@@ -26,7 +26,8 @@ def _net():
                       n_levels=2, pooling_type="max", gpu_ids=[torch.device(DEV)]).train()
 
 
-def test_graphed_step_equals_eager_step():
+@pytest.mark.parametrize("prefetch", [False, True])
+def test_graphed_step_equals_eager_step(prefetch):
     from stinet_b200.engine import GraphedTrainStep, batch_signature
     batches = [_make(49), _make(50), _make(49)]
     assert batch_signature(batches[0]) == batch_signature(batches[1])
@@ -47,8 +48,14 @@ def test_graphed_step_equals_eager_step():
                 for v in g.values():
                     if torch.is_tensor(v):
                         v.zero_()
-            for b in batches:
-                losses.append(float(step(b.pin_memory()).item()))
+            pinned = [b.pin_memory() for b in batches]
+            if prefetch:                                  # loader pattern: batch k+1 moves H2D while step k runs
+                assert step.prefetch(pinned[0])
+            for i, b in enumerate(pinned):
+                loss = step(b)
+                if prefetch and i + 1 < len(pinned):
+                    assert step.prefetch(pinned[i + 1])
+                losses.append(float(loss.item()))
             assert step.captures == 1 and step.replayed_launches > 0
         else:
             for b in batches:
