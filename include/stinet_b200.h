@@ -68,6 +68,14 @@ size_t stinet_csr_workspace_bytes(int64_t n_rows, int64_t n_items);
 int stinet_csr_build(const int64_t* key, const int64_t* other, int64_t n_items, int64_t n_rows, int32_t* rowptr,
                      int32_t* perm, int32_t* col, int32_t* key32, int32_t* status, void* workspace,
                      size_t workspace_bytes, stinet_stream_t stream);
+/* Block-diagonal batching of structures built once per sample (the offsets are those of
+ * HierarchicalData.__inc__, utils/data_utils.py:29-42, which the reference applies to the COO tensors in collate):
+ *   dst[dst_off[p] + i] = src[p][i] + add[p]   for i < len[p], p < n_parts.
+ * `src`, `len`, `dst_off`, `add` are HOST arrays (they travel in the launch parameters); src[p] and dst are device
+ * pointers.  rowptr parts pass len = n_rows (the last part n_rows + 1) and add = edge offset; col / member parts pass
+ * add = vertex offset. */
+int stinet_concat_i32(const int32_t* const* src, const int64_t* len, const int64_t* dst_off, const int32_t* add,
+                      int n_parts, int32_t* dst, stinet_stream_t stream);
 /* ---- aggregation over CSR rows (replaces PyG propagate's scatter(msg, edge_index[1], reduce=...) =
  * torch_scatter.scatter_{sum,mean,max}; call sites edge_conv_filter.py:57 (mean), sage_conv_filter.py:75 (mean),
  * utils/metrics/graph_metrics.py:12 (add)).  out[i,:] = reduce_{k in row i} x[col[k],:]; mean = sum/max(deg,1);

@@ -181,6 +181,38 @@ __global__ void csr_gather_col(const int64_t* __restrict__ other, const int32_t*
   }
 }
 
+// Block-diagonal batching of per-sample structures: part p of the destination is src[p][0..len) + add[p].
+// Up to kConcatParts parts travel by value in the launch parameters (no device-side pointer table, no H2D copy).
+constexpr int kConcatParts = 32;
+struct ConcatArgs {
+  const int32_t* src[kConcatParts];
+  int64_t len[kConcatParts];
+  int64_t dst_off[kConcatParts];
+  int32_t add[kConcatParts];
+  int n_parts;
+};
+__global__ void __launch_bounds__(256) concat_i32_kernel(const __grid_constant__ ConcatArgs a, int32_t* __restrict__ dst) {
+  const int p = blockIdx.y;
+  const int32_t* __restrict__ src = a.src[p];
+  int32_t* __restrict__ out = dst + a.dst_off[p];
+  const int64_t n = a.len[p];
+  const int32_t add = a.add[p];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // 128-bit body when both sides are 16-byte aligned, scalar otherwise (offsets are arbitrary vertex / edge counts)
+  if ((((uintptr_t)src | (uintptr_t)out) & 15u) == 0) {
+    const int64_t n4 = n >> 2;
+    for (int64_t k = i; k < n4; k += stride) {
+      int4 v = reinterpret_cast<const int4*>(src)[k];
+      v.x += add; v.y += add; v.z += add; v.w += add;
+      reinterpret_cast<int4*>(out)[k] = v;
+    }
+    for (int64_t k = (n4 << 2) + i; k < n; k += stride) out[k] = src[k] + add;
+  } else {
+    for (int64_t k = i; k < n; k += stride) out[k] = src[k] + add;
+  }
+}
+
 struct CsrWorkspace {
   int32_t *cnt, *cursor, *chunk, *big_rows, *n_big, *tmp;
   size_t bytes;
@@ -243,4 +275,33 @@ extern "C" int stinet_csr_build(const int64_t* key, const int64_t* other, int64_
     if (other) K(csr_gather_col<<<grid_items, threads, 0, stream>>>(other, perm, n_items, n_rows, col, status));
   }
   return check_launch("csr_build");
+}
+
+extern "C" int stinet_concat_i32(const int32_t* const* src, const int64_t* len, const int64_t* dst_off,
+                                 const int32_t* add, int n_parts, int32_t* dst, stinet_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(n_parts >= 0, STINET_ERR_ARG, "concat_i32: negative part count");
+  if (n_parts == 0) return STINET_OK;
+  STINET_REQUIRE(src && len && dst_off && add && dst, STINET_ERR_ARG, "concat_i32: null pointer");
+  for (int p0 = 0; p0 < n_parts; p0 += kConcatParts) {
+    ConcatArgs a;
+    a.n_parts = n_parts - p0 < kConcatParts ? n_parts - p0 : kConcatParts;
+    int64_t longest = 0;
+    for (int p = 0; p < kConcatParts; ++p) {
+      const bool on = p < a.n_parts;
+      a.src[p] = on ? src[p0 + p] : nullptr;
+      a.len[p] = on ? len[p0 + p] : 0;
+      a.dst_off[p] = on ? dst_off[p0 + p] : 0;
+      a.add[p] = on ? add[p0 + p] : 0;
+      STINET_REQUIRE(!on || (a.len[p] >= 0 && a.dst_off[p] >= 0 && (a.len[p] == 0 || a.src[p])), STINET_ERR_ARG,
+                     "concat_i32: bad part %d", p0 + p);
+      if (a.len[p] > longest) longest = a.len[p];
+    }
+    if (longest == 0) continue;
+    int gx = wave_grid(longest, 256 * 8, 4) / a.n_parts;     // ~4 CTAs per SM over all parts
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)a.n_parts);
+    K(concat_i32_kernel<<<grid, 256, 0, stream>>>(a, dst));
+  }
+  return check_launch("concat_i32");
 }

@@ -14,7 +14,6 @@ namespace stinet {
 
 constexpr int BM = 128, BN = 64, BK = 16;
 constexpr int kGemmThreads = 256;
-constexpr int kColsumRows = 512;
 
 struct GemmArgs {
   const float* A; int64_t lda;     // A'(i,t): A_TC ? A[i*lda+t] : A[t*lda+i]
@@ -182,45 +181,108 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
   }
 }
 
+// the same for many splits of a small output (wgrad of the fine levels: up to 296 partials of a 64 x 128 matrix): the
+// 8 warps of a CTA each sum every 8th split of 128 consecutive elements (128-bit loads), then warp 0 adds the eight
+// partial sums in fixed order.  IJ % 4 == 0, J % 4 == 0, out rows 16-byte aligned.
+__global__ void __launch_bounds__(256) splitk_reduce_wide_kernel(const float* __restrict__ part, int splits, int64_t IJ, int J,
+                                                                 float* __restrict__ out, int64_t ldo) {
+  __shared__ float4 sm[8][32];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t idx = ((int64_t)blockIdx.x * 32 + lane) * 4;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (idx < IJ) {
+    for (int s0 = wrp; s0 < splits; s0 += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int sp = s0 + 8 * u;
+        v[u] = sp < splits ? ld_stream(reinterpret_cast<const float4*>(part + (int64_t)sp * IJ + idx))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { t.x += v[u].x; t.y += v[u].y; t.z += v[u].z; t.w += v[u].w; }
+    }
+  }
+  sm[wrp][lane] = t;
+  __syncthreads();
+  if (wrp == 0 && idx < IJ) {
+    float4 r = sm[0][lane];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) { const float4 q = sm[y][lane]; r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
+    const int64_t i = idx / J;
+    const int j = (int)(idx - i * J);
+    *reinterpret_cast<float4*>(out + i * ldo + j) = r;
+  }
+}
+
 // dbias: masked column sums of dC in two deterministic stages.
-// stage 1: partial[chunk][n] = sum over the chunk's rows of dC[m,n] * mask(m); CTA = 32 column lanes x 8 row lanes,
-//          each column lane owns 4 (VEC) or 1 columns, rows are read as full 512 B / 128 B segments.
-template <bool VEC>
+// stage 1: partial[chunk][n] = sum over the chunk's rows of dC[m,n] * mask(m).  Vector form: CTA = CL column lanes
+//          (4 columns each: 128-bit loads, full 512 B / 256 B row segments) x 256/CL row lanes, four rows in flight
+//          per thread; the rows of a chunk are chosen by the host so that even a 1296-row matrix fills the SMs.
+template <int CL>
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const float* __restrict__ x, int64_t ldx,
+                                                                 const int32_t* __restrict__ rowmask, int64_t M, int N,
+                                                                 int rows_per_chunk, float* __restrict__ part) {
+  constexpr int RL = 256 / CL;
+  __shared__ float4 sm[RL][CL];
+  const int tx = threadIdx.x % CL, ty = threadIdx.x / CL;
+  const int n0 = (blockIdx.x * CL + tx) * 4;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t m1 = min(M, m0 + rows_per_chunk);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n0 < N) {
+    for (int64_t m = m0 + ty; m < m1; m += 4 * RL) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t mm = m + u * RL;
+        const bool on = mm < m1 && (rowmask == nullptr || rowmask[mm] > 0);
+        v[u] = on ? ld_stream(reinterpret_cast<const float4*>(x + mm * ldx + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n0 < N) {
+    float4 t = sm[0][tx];
+#pragma unroll
+    for (int y = 1; y < RL; ++y) { const float4 q = sm[y][tx]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+    *reinterpret_cast<float4*>(part + (int64_t)blockIdx.y * N + n0) = t;      // N % 4 == 0 on this path
+  }
+}
+// scalar form for widths / pitches that are not multiples of four floats
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t ldx,
                                                              const int32_t* __restrict__ rowmask, int64_t M, int N,
-                                                             float* __restrict__ part) {
-  constexpr int W = VEC ? 4 : 1;
-  __shared__ float sm[8][32 * W + 1];
+                                                             int rows_per_chunk, float* __restrict__ part) {
+  __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n0 = (blockIdx.x * 32 + tx) * W;
-  const int64_t m0 = (int64_t)blockIdx.y * kColsumRows;
-  const int64_t m1 = min(M, m0 + kColsumRows);
-  float acc[W];
-#pragma unroll
-  for (int w = 0; w < W; ++w) acc[w] = 0.f;
+  const int n0 = blockIdx.x * 32 + tx;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t m1 = min(M, m0 + rows_per_chunk);
+  float acc = 0.f;
   if (n0 < N) {
     for (int64_t m = m0 + ty; m < m1; m += 8) {
       if (rowmask && rowmask[m] <= 0) continue;
-      if (VEC) {
-        const float4 v = *reinterpret_cast<const float4*>(x + m * ldx + n0);
-        acc[0] += v.x; acc[1 % W] += v.y; acc[2 % W] += v.z; acc[3 % W] += v.w;
-      } else {
-        acc[0] += x[m * ldx + n0];
-      }
+      acc += x[m * ldx + n0];
     }
   }
-#pragma unroll
-  for (int w = 0; w < W; ++w) sm[ty][tx * W + w] = acc[w];
+  sm[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && n0 < N) {
+    float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-      float t = 0.f;
-#pragma unroll
-      for (int y = 0; y < 8; ++y) t += sm[y][tx * W + w];
-      if (n0 + w < N) part[(int64_t)blockIdx.y * N + n0 + w] = t;
-    }
+    for (int y = 0; y < 8; ++y) t += sm[y][tx];
+    part[(int64_t)blockIdx.y * N + n0] = t;
   }
+}
+// rows per stage-1 chunk: 512 for tall matrices, fewer (down to 32) when that is needed to put ~4 CTAs on every SM
+static int colsum_rows(int64_t M, int64_t N) {
+  const int64_t col_ctas = ceil_div(N, 128);
+  int r = 512;
+  while (r > 32 && col_ctas * ceil_div(M > 0 ? M : 1, r) < 4 * kSMs) r >>= 1;
+  return r;
 }
 // stage 2: out[n] = sum_chunks partial[chunk][n]; 32 column lanes x 32 chunk lanes, fixed-order tree over the lanes
 __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ part, int chunks, int N,
@@ -368,7 +430,7 @@ static GemmWs carve_gemm(void* base, int64_t M, int64_t N, int64_t K, int precis
   if (sf > 1 && (size_t)sf * rows * N > sk_elems) sk_elems = (size_t)sf * rows * N;          // fwd partials
   if (sd > 1 && (size_t)sd * rows * K > sk_elems) sk_elems = (size_t)sd * rows * K;          // dgrad partials
   const size_t sk = up(sizeof(float) * sk_elems);
-  const size_t cs = up(sizeof(float) * (size_t)ceil_div(rows, kColsumRows) * N);
+  const size_t cs = up(sizeof(float) * (size_t)ceil_div(rows, colsum_rows(rows, N)) * N);
   const bool x3 = precision == STINET_PREC_BF16X3;
   const bool b16 = precision == STINET_PREC_BF16 || x3;
   const size_t planes = x3 ? 2 : 1;
@@ -562,7 +624,9 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
     if (ok && tc::eligible(p)) {
       int rc = tc::run(p, s);
       if (rc) return rc;
-      if (sp.splits > 1)
+      if (sp.splits >= 16 && !(K & 3) && !(ldw & 3) && aligned16(dW))
+        K(splitk_reduce_wide_kernel<<<(unsigned)ceil_div(N * K, 128), 256, 0, s>>>(w.splitk, sp.splits, N * K, (int)K, dW, ldw));
+      else if (sp.splits > 1)
         K(splitk_reduce_kernel<<<wave_grid(N * K, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, N * K, (int)K, dW, ldw, nullptr,
                                                                         nullptr));
       done = true;
@@ -583,14 +647,18 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
     }
   }
   if (dbias) {
-    const int chunks = (int)ceil_div(M > 0 ? M : 1, kColsumRows);
+    const int rpc = colsum_rows(M > 0 ? M : 1, N);
+    const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
     const bool vec = !(N & 3) && !(ldc & 3) && aligned16(dC);
-    if (vec) {
+    if (vec && N > 64) {
       dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
-      K(colsum_partial_kernel<true><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, w.colsum));
+      K(colsum_partial_vec_kernel<32><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, w.colsum));
+    } else if (vec) {
+      dim3 g2((unsigned)ceil_div(N, 64), (unsigned)chunks);
+      K(colsum_partial_vec_kernel<16><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, w.colsum));
     } else {
       dim3 g2((unsigned)ceil_div(N, 32), (unsigned)chunks);
-      K(colsum_partial_kernel<false><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, w.colsum));
+      K(colsum_partial_kernel<<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, w.colsum));
     }
     K(colsum_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(w.colsum, chunks, (int)N, dbias));
   }

@@ -79,12 +79,13 @@ class GraphBatch:
         out = GraphBatch()
         for k in self.keys:
             v = self.__dict__[k]
-            out.__dict__[k] = v.pin_memory() if torch.is_tensor(v) else v
+            out.__dict__[k] = v.pin_memory() if (torch.is_tensor(v) and not v.is_cuda) else v
         out.__dict__["_nv_host"] = self._host_num_vertices()
         return out
 
-    def tensor_bytes(self) -> int:
-        return sum(v.numel() * v.element_size() for v in self.__dict__.values() if torch.is_tensor(v))
+    def tensor_bytes(self, host_only: bool = False) -> int:
+        return sum(v.numel() * v.element_size() for v in self.__dict__.values()
+                   if torch.is_tensor(v) and not (host_only and v.is_cuda))
 
 
 def _inc(sample: GraphBatch, key: str) -> int:
@@ -112,12 +113,16 @@ def _cat_dim(key: str):
     return 0
 
 
-def collate(samples: Iterable[GraphBatch]) -> GraphBatch:
-    """Batch a list of single-graph samples the way PyG's DataLoader batches HierarchicalData."""
+def collate(samples: Iterable[GraphBatch], keep_index: bool = True) -> GraphBatch:
+    """Batch a list of single-graph samples the way PyG's DataLoader batches HierarchicalData.
+    keep_index=False leaves the COO edge sets and trace maps out (their structure is cached per sample and batched
+    on the device by stinet_b200.structure.attach_batch_structure)."""
     samples = list(samples)
     out = GraphBatch()
     fields: Dict[str, object] = {}
     for key in samples[0].keys:
+        if not keep_index and (key == "edge_index" or key.startswith("hierarchy_")):
+            continue
         vals, inc = [], 0
         for s in samples:
             v = s[key]

@@ -126,15 +126,18 @@ class GraphedTrainStep:
             self.reducer.overlap = False                 # hooks must not launch collectives inside the capture
         n0 = _abi.query("stinet_launch_count")
         try:
+            # with a process group alive, NCCL's watchdog thread polls CUDA events while we capture: only this thread's
+            # calls may be policed by the capture (the mode PyTorch documents for DDP + CUDA graphs)
+            mode = "thread_local" if self.world > 1 else "global"
             c.graph_a = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(c.graph_a):
+            with torch.cuda.graph(c.graph_a, capture_error_mode=mode):
                 c.loss = self._fwd_bwd(c.static)
                 if self.world == 1 and self.opt is not None:
                     self.opt.step()
             c.graph_b = None
             if self.world > 1 and self.opt is not None:
                 c.graph_b = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(c.graph_b, pool=c.graph_a.pool()):
+                with torch.cuda.graph(c.graph_b, pool=c.graph_a.pool(), capture_error_mode=mode):
                     self.opt.step()
         finally:
             if self.reducer is not None:
@@ -143,21 +146,32 @@ class GraphedTrainStep:
         self.captures += 1
         return c
 
-    def prefetch(self, batch) -> bool:
+    def prefetch(self, batch, structs=None) -> bool:
         """Start moving the NEXT batch (pinned host memory) to the device on a copy stream while the current step is
         still running; the following `step(batch)` call with the same object then only pays one device-to-device copy.
-        What a DataLoader with pin_memory + a prefetching collate thread gives the reference trainer.  Returns False
-        (and does nothing) for a batch shape that has not been captured yet."""
+        What a DataLoader with pin_memory + a prefetching collate thread gives the reference trainer.
+        `structs`: the samples' cached SampleStructures (stinet_b200.structure) -- their block-diagonal concatenation
+        is then done here too, on the copy stream, and attached to `batch`.
+        Returns False (nothing staged) for a batch shape that has not been captured yet."""
+        dev = next(self.net.parameters()).device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        if any(v.is_cuda for _, v in _tensor_items(batch)):  # device-resident fields were produced on the compute stream
+            self._copy_stream.wait_stream(cur)
+        if structs is not None:
+            from .structure import attach_batch_structure
+            with torch.cuda.stream(self._copy_stream):
+                attach_batch_structure(batch, structs, dev)
         c = self._cache.get(batch_signature(batch))
         if c is None:
+            if structs is not None:
+                cur.wait_stream(self._copy_stream)       # the attached arrays will be read by the capturing call
             return False
-        dev = c.flat.device
         if c.staging is None:
             c.staging = torch.empty_like(c.flat)
             c.ready, c.free = torch.cuda.Event(), torch.cuda.Event()
-            c.free.record(torch.cuda.current_stream(dev))
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=dev)
+            c.free.record(cur)
         self._copy_stream.wait_event(c.free)             # the previous staged batch has been consumed
         with torch.cuda.stream(self._copy_stream):
             for k, v in c.views(c.staging).items():

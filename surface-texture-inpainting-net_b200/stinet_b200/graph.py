@@ -61,6 +61,16 @@ class EdgeCSR:
         self.rowptr_t, self.eid_t, self.col_t, _ = build_csr(self._dst, self._src, self.n, status=status)
         self._by_source = None
 
+    @classmethod
+    def from_arrays(cls, n: int, rowptr_t, col_t, eid_t, rowptr_s, col_s, eid_s) -> "EdgeCSR":
+        """Wrap arrays that already exist (stinet_b200.structure: built once per sample, concatenated per batch)."""
+        self = cls.__new__(cls)
+        self.n, self.e = int(n), int(col_t.numel())
+        self._src = self._dst = self._status = None
+        self.rowptr_t, self.col_t, self.eid_t = rowptr_t, col_t, eid_t
+        self._by_source = (rowptr_s, col_s, eid_s)
+        return self
+
     def by_source(self):
         """rowptr_s, col_s (= target vertex of each out-edge), eid_s -- only needed by backward passes."""
         if self._by_source is None:
@@ -83,6 +93,13 @@ class ClusterCSR:
         self.n_fine, self.n_coarse = int(trace.numel()), int(n_coarse)
         self.rowptr, self.member, _, self.trace32 = build_csr(trace.contiguous(), None, self.n_coarse,
                                                              want_key32=True, status=status)
+
+    @classmethod
+    def from_arrays(cls, n_fine: int, n_coarse: int, rowptr, member, trace32) -> "ClusterCSR":
+        self = cls.__new__(cls)
+        self.n_fine, self.n_coarse = int(n_fine), int(n_coarse)
+        self.rowptr, self.member, self.trace32 = rowptr, member, trace32
+        return self
 
 
 _SEG_TABLES: Dict[tuple, tuple] = {}
@@ -169,16 +186,24 @@ class GraphCache:
     # -- structure ------------------------------------------------------------------------------------------
     def edges(self, key: str, level: int) -> EdgeCSR:
         if key not in self._edges:
-            ei = self._sample.edge_index if key == "edge_index" else self._sample[key]
-            self._edges[key] = EdgeCSR(ei, self.totals[level], self.status)
+            from .structure import prebuilt_edges
+            pre = prebuilt_edges(self._sample, key, self.totals[level])     # cached per sample, batched by concatenation
+            if pre is None:
+                ei = self._sample.edge_index if key == "edge_index" else self._sample[key]
+                pre = EdgeCSR(ei, self.totals[level], self.status)
+            self._edges[key] = pre
         return self._edges[key]
 
     def cluster(self, level: int) -> ClusterCSR:
         """trace map level-1 -> level."""
         if level not in self._clusters:
-            tr = self._sample[f"hierarchy_trace_index_{level}"]
-            assert tr.numel() == self.totals[level - 1]
-            self._clusters[level] = ClusterCSR(tr, self.totals[level], self.status)
+            from .structure import prebuilt_cluster
+            pre = prebuilt_cluster(self._sample, level, self.totals[level - 1], self.totals[level])
+            if pre is None:
+                tr = self._sample[f"hierarchy_trace_index_{level}"]
+                assert tr.numel() == self.totals[level - 1]
+                pre = ClusterCSR(tr, self.totals[level], self.status)
+            self._clusters[level] = pre
         return self._clusters[level]
 
     def graph_id(self, level: int) -> Optional[torch.Tensor]:

@@ -1,0 +1,171 @@
+"""Graph structure cached per SAMPLE and batched block-diagonally.
+
+The topology of a mesh crop / scene / image grid never changes between epochs, yet a step that starts from the
+collated COO tensors has to re-sort every edge set and trace map of the batch (`stinet_csr_build`, ~4 % of a cfg2
+step) and to move the int64 index tensors host-to-device (~70 % of the step's H2D bytes).  Here the CSR / cluster CSR
+of each sample is built ONCE on the device (`SampleStructure.build`, same kernel), kept in HBM next to the dataset
+(a 40 k-vertex crop needs ~5 MB), and a batch's structure is the block-diagonal concatenation of its samples'
+arrays with the offsets of the reference's collate (utils/data_utils.py:29-42: edge_index += cumulative N_0,
+hierarchy_edge_index_l / hierarchy_trace_index_l += cumulative N_l) -- a handful of `stinet_concat_i32` launches
+that stream each array once.  The result is bit-identical to building from the collated batch
+(tests/test_gpu_structure.py), because grouping is stable and samples occupy disjoint, ascending index ranges.
+
+    structs = [SampleStructure.build(s, n_levels, device) for s in samples]        # once, e.g. in Dataset.__init__
+    batch = collate(samples, keep_index=False)                                     # features only, no COO tensors
+    attach_batch_structure(batch, structs)                                         # device, per step
+    out = net(batch.to(device))                                                    # GraphCache picks the arrays up
+
+The arrays travel on the batch as ordinary tensor fields named `csr:<edge key>:<array>` / `ccsr:<level>:<array>`,
+so `GraphedTrainStep` copies them into its static inputs like any other field and the captured graph contains no
+structure-build kernels at all.
+
+Dilated edge sets (`hierarchy_dil_{d}_edge_index_{l}`) are offset by the level-l vertex counts here.  The reference's
+collate offsets them by the level-0 node count (a PyG default, data_utils.py:42), which is only meaningful for
+batch size 1 -- the only way the reference uses them; for B = 1 both agree.
+"""
+from __future__ import annotations
+
+import ctypes
+import re
+from typing import Dict, List, Sequence
+
+import torch
+
+from . import _abi
+from .graph import ClusterCSR, EdgeCSR, _stream
+
+_EDGE_KEY = re.compile(r"^(edge_index|hierarchy_edge_index_(\d+)|hierarchy_dil_\d+_edge_index_(\d+))$")
+_EDGE_ARRAYS = ("rowptr_t", "col_t", "eid_t", "rowptr_s", "col_s", "eid_s")
+_CLUSTER_ARRAYS = ("rowptr", "member", "trace32")
+
+
+def edge_key_level(key: str):
+    """Level whose vertices an edge set connects, or None if `key` is not an edge set."""
+    m = _EDGE_KEY.match(key)
+    if not m:
+        return None
+    return int(m.group(2) or m.group(3) or 0)
+
+
+class SampleStructure:
+    """CSR by target and by source of every edge set, cluster CSR of every trace map, of ONE graph (device int32)."""
+
+    def __init__(self, n_vertices: List[int]):
+        self.n_vertices = list(n_vertices)                 # [L+1]
+        self.edges: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.n_edges: Dict[str, int] = {}
+        self.clusters: Dict[int, Dict[str, torch.Tensor]] = {}
+
+    @staticmethod
+    def build(sample, n_levels: int, device) -> "SampleStructure":
+        """sample: single-graph HierarchicalData-like object (host or device); runs `stinet_csr_build` per structure."""
+        nv = sample.num_vertices
+        nv = [int(v) for v in (nv.tolist() if torch.is_tensor(nv) else nv)]
+        st = SampleStructure(nv[:n_levels + 1])
+        keys = sample.keys() if callable(getattr(sample, "keys", None)) else sample.keys
+        for key in keys:
+            lvl = edge_key_level(key)
+            if lvl is None or lvl > n_levels:
+                continue
+            ei = sample[key].to(device)
+            csr = EdgeCSR(ei, nv[lvl])
+            rowptr_s, col_s, eid_s = csr.by_source()
+            st.edges[key] = dict(rowptr_t=csr.rowptr_t, col_t=csr.col_t, eid_t=csr.eid_t, rowptr_s=rowptr_s,
+                                 col_s=col_s, eid_s=eid_s)
+            st.n_edges[key] = csr.e
+        for lvl in range(1, n_levels + 1):
+            tr = sample[f"hierarchy_trace_index_{lvl}"].to(device)
+            cl = ClusterCSR(tr, nv[lvl])
+            st.clusters[lvl] = dict(rowptr=cl.rowptr, member=cl.member, trace32=cl.trace32)
+        return st
+
+    def nbytes(self) -> int:
+        t = [a for d in self.edges.values() for a in d.values()] + [a for d in self.clusters.values() for a in d.values()]
+        return sum(a.numel() * 4 for a in t)
+
+
+def _concat(parts: Sequence[torch.Tensor], lens: Sequence[int], dst_offs: Sequence[int], adds: Sequence[int],
+            total: int, device) -> torch.Tensor:
+    out = torch.empty(total, dtype=torch.int32, device=device)
+    n = len(parts)
+    if n == 0 or total == 0:
+        return out
+    src = (ctypes.c_void_p * n)(*[p.data_ptr() for p in parts])
+    ln = (ctypes.c_int64 * n)(*[int(x) for x in lens])
+    off = (ctypes.c_int64 * n)(*[int(x) for x in dst_offs])
+    add = (ctypes.c_int32 * n)(*[int(x) for x in adds])
+    _abi.call("stinet_concat_i32", src, ln, off, add, n, out.data_ptr(), _stream(),
+              cost=(8 * total, 0, ""))
+    return out
+
+
+def _cum(xs: Sequence[int]) -> List[int]:
+    out = [0]
+    for x in xs:
+        out.append(out[-1] + int(x))
+    return out
+
+
+def batch_structure(structs: Sequence[SampleStructure], device) -> Dict[str, torch.Tensor]:
+    """Block-diagonal concatenation -> {field name: int32 device tensor} for `attach_batch_structure`."""
+    B = len(structs)
+    assert B >= 1
+    L = len(structs[0].n_vertices) - 1
+    voff = [_cum([s.n_vertices[l] for s in structs]) for l in range(L + 1)]       # [level][b]
+    out: Dict[str, torch.Tensor] = {}
+    for key in structs[0].edges:
+        lvl = edge_key_level(key)
+        eoff = _cum([s.n_edges[key] for s in structs])
+        nv = [s.n_vertices[lvl] for s in structs]
+        ne = [s.n_edges[key] for s in structs]
+        rows = [n + (1 if b == B - 1 else 0) for b, n in enumerate(nv)]            # the last part brings the end sentinel
+        for name in _EDGE_ARRAYS:
+            parts = [s.edges[key][name] for s in structs]
+            if name.startswith("rowptr"):
+                t = _concat(parts, rows, voff[lvl][:B], eoff[:B], voff[lvl][B] + 1, device)
+            elif name.startswith("col"):
+                t = _concat(parts, ne, eoff[:B], voff[lvl][:B], eoff[B], device)
+            else:                                                                  # eid: position in the collated edge list
+                t = _concat(parts, ne, eoff[:B], eoff[:B], eoff[B], device)
+            out[f"csr:{key}:{name}"] = t
+    for lvl in structs[0].clusters:
+        fine, coarse = voff[lvl - 1], voff[lvl]
+        nf = [s.n_vertices[lvl - 1] for s in structs]
+        nc = [s.n_vertices[lvl] for s in structs]
+        rows = [n + (1 if b == B - 1 else 0) for b, n in enumerate(nc)]
+        parts = {n: [s.clusters[lvl][n] for s in structs] for n in _CLUSTER_ARRAYS}
+        out[f"ccsr:{lvl}:rowptr"] = _concat(parts["rowptr"], rows, coarse[:B], fine[:B], coarse[B] + 1, device)
+        out[f"ccsr:{lvl}:member"] = _concat(parts["member"], nf, fine[:B], fine[:B], fine[B], device)
+        out[f"ccsr:{lvl}:trace32"] = _concat(parts["trace32"], nf, fine[:B], coarse[:B], fine[B], device)
+    return out
+
+
+def attach_batch_structure(batch, structs: Sequence[SampleStructure], device=None):
+    """Concatenate the samples' structures on the device and hang the arrays on `batch` (returned for chaining)."""
+    if device is None:
+        device = next(iter(structs[0].clusters.values()))["rowptr"].device if structs[0].clusters else \
+            next(iter(structs[0].edges.values()))["rowptr_t"].device
+    for k, v in batch_structure(structs, device).items():
+        batch.__dict__[k] = v
+    batch.__dict__.pop("_stinet_cache", None)
+    return batch
+
+
+def prebuilt_edges(sample, key: str, n: int):
+    """EdgeCSR over the batch's prebuilt arrays, or None if the batch does not carry them."""
+    d = getattr(sample, "__dict__", {})
+    rp = d.get(f"csr:{key}:rowptr_t")
+    if rp is None:
+        return None
+    arr = {name: d[f"csr:{key}:{name}"] for name in _EDGE_ARRAYS}
+    assert rp.numel() == n + 1, f"prebuilt structure of {key} has {rp.numel() - 1} rows, level has {n}"
+    return EdgeCSR.from_arrays(n, **arr)
+
+
+def prebuilt_cluster(sample, level: int, n_fine: int, n_coarse: int):
+    d = getattr(sample, "__dict__", {})
+    rp = d.get(f"ccsr:{level}:rowptr")
+    if rp is None:
+        return None
+    assert rp.numel() == n_coarse + 1 and d[f"ccsr:{level}:member"].numel() == n_fine
+    return ClusterCSR.from_arrays(n_fine, n_coarse, rp, d[f"ccsr:{level}:member"], d[f"ccsr:{level}:trace32"])

@@ -269,10 +269,15 @@ def grid_sample(size: int = 128, n_levels: int = 2, seed: int = 49, circle_radiu
     return s
 
 
-def make_batch(kind: str, batch_size: int, n_levels: int, seed: int = 49, **kw) -> GraphBatch:
-    """kind: 'grid' (size=), 'icosphere' (subdiv=), 'plane' (rows=, cols=).  Sample b uses seed+b."""
+def make_samples(kind: str, batch_size: int, n_levels: int, seed: int = 49, **kw) -> List[GraphBatch]:
+    """The single-graph samples `make_batch` collates.  kind: 'grid' (size=), 'icosphere' (subdiv=), 'plane' (rows=,
+    cols=).  Sample b uses seed+b."""
     fn = {"grid": grid_sample, "icosphere": icosphere_sample, "plane": plane_sample}[kind]
-    return collate([fn(n_levels=n_levels, seed=seed + b, **kw) for b in range(batch_size)])
+    return [fn(n_levels=n_levels, seed=seed + b, **kw) for b in range(batch_size)]
+
+
+def make_batch(kind: str, batch_size: int, n_levels: int, seed: int = 49, **kw) -> GraphBatch:
+    return collate(make_samples(kind, batch_size, n_levels, seed, **kw))
 
 
 def paper_graph18() -> Tuple[torch.Tensor, int]:
