@@ -131,6 +131,7 @@ class Segments:
             cnt = [max(self.n_rows, 1)]
             self.gid = None
             self.consistent = True
+            self.true_ptr = [0, self.n_rows]
         else:
             self.n_seg = len(counts)
             # same call as the reference (fastinstancenorm.py:53), evaluated on the host
@@ -140,7 +141,9 @@ class Segments:
             for c in counts:
                 true_ptr.append(true_ptr[-1] + int(c))
             self.consistent = (true_ptr == slice_ptr)
+            self.true_ptr = true_ptr
             self.gid = gid
+        self.slice_ptr_host = list(slice_ptr)
         self.max_seg_rows = max(b - a for a, b in zip(slice_ptr[:-1], slice_ptr[1:]))
         self.slice_ptr, self.cnt = _segment_tables(tuple(slice_ptr), tuple(cnt), torch.device(device))
 

@@ -383,9 +383,9 @@ class NormActResFn(Function):
             dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
             if ctx.use_norm:
                 if not seg.consistent:
-                    raise _abi.StinetError(
-                        "instance-norm backward needs graphs of equal size in a batch: the reference's linspace slices "
-                        "(fastinstancenorm.py:53) do not match the true graph boundaries here")
+                    dx = _ragged_norm_backward(x, dout, mean, rstd, seg, ctx.act)
+                    dres = dout if (ctx.has_res and ctx.needs_input_grad[1]) else None
+                    return dx, dres, None, None, None, None
                 nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
                 ws = _ws(nb, x.device)
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, seg.n_seg,
@@ -398,6 +398,40 @@ class NormActResFn(Function):
                           None, None, None, None, ctx.act, dx.data_ptr(), c, None, 0, _stream())
         dres = dout if (ctx.has_res and ctx.needs_input_grad[1]) else None
         return dx, dres, None, None, None, None
+
+
+def _ragged_norm_backward(x, dout, mean, rstd, seg: Segments, act: int):
+    """Gradient of the reference's per-graph norm when its `linspace` slices (fastinstancenorm.py:53) cut across the
+    true graph boundaries (graphs of different size in one batch).  There the statistics of graph g are sums over
+    SLICE g divided by the true count of graph g, looked up through `batch` (:60-82), so the derivative couples rows
+    of neighbouring graphs.  The reference never trains in this regime (3D: batch 1; 2D: equal-size images), so this is
+    a short composite of device tensor ops (segment sums over a handful of contiguous row ranges) rather than a
+    dedicated kernel; the equal-size case runs on stinet_segnorm_bwd.
+        y_i = (x_i - m[g_i]) r[g_i],  m[g] = sum_{slice g} x / cnt_g,  v[g] = sum_{slice g} (x - m[gid])^2 / cnt_g"""
+    tp, sp = seg.true_ptr, seg.slice_ptr_host
+    B = seg.n_seg
+    gid = seg.gid.long()
+    slice_len = torch.tensor([sp[b + 1] - sp[b] for b in range(B)], device=x.device)
+    m, r = mean.index_select(0, gid), rstd.index_select(0, gid)
+    xc = x - m
+    if act == ACT_ELU:
+        v = xc * r
+        dy = dout * torch.where(v > 0, torch.ones_like(v), torch.exp(v))
+    else:
+        dy = dout
+    cnt = seg.cnt.view(-1, 1)
+
+    def by_graph(t):          # sums over the rows whose graph id is g (contiguous: collate keeps graphs in order)
+        return torch.stack([t[tp[b]:tp[b + 1]].sum(0) for b in range(B)])
+
+    def by_slice(table):      # value of slice s(i) for every row i
+        return torch.repeat_interleave(table, slice_len, dim=0)
+
+    dr = by_graph(dy * xc)                                   # dL/dr[g]
+    dv = -0.5 * dr * rstd ** 3                               # dL/dv[g]
+    dxc = dy * r + 2.0 * xc * by_slice(dv / cnt)             # total derivative w.r.t. xc_i
+    dm = -by_graph(dxc)                                      # dL/dm[g]
+    return dxc + by_slice(dm / cnt)
 
 
 def norm_act_res(x, residual, seg, use_norm=True, act=ACT_ELU, eps=1e-5):

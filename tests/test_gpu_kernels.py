@@ -236,7 +236,7 @@ def test_graph_id_pooling_int():
 @pytest.mark.parametrize("layout", ["single", "equal", "ragged", "equal_mid", "single_long", "equal_long"])
 def test_instance_norm_elu_residual(c, layout):
     from stinet_b200.models.modules import FastInstanceNorm
-    from stinet_b200._abi import ACT_ELU, StinetError
+    from stinet_b200._abi import ACT_ELU
     g = torch.Generator().manual_seed(5)
     counts = {"single": [700], "equal": [300, 300, 300], "ragged": [500, 77, 323], "equal_mid": [3000, 3000],
               "single_long": [17001], "equal_long": [16500, 16500]}[layout]
@@ -252,11 +252,7 @@ def test_instance_norm_elu_residual(c, layout):
     xd, rd = x.to(DEV).requires_grad_(True), res.to(DEV).requires_grad_(True)
     out = norm(xd, None if batch is None else batch.to(DEV), rd, ACT_ELU)
     assert rel_err(out, ref) <= TOL
-    if layout == "ragged":
-        with pytest.raises(StinetError):            # documented deviation: backward needs equal-size graphs
-            out.backward(go.to(DEV))
-        return
-    out.backward(go.to(DEV))
+    out.backward(go.to(DEV))                        # ragged: composite backward of the linspace-slice quirk
     assert rel_err(xd.grad, xr.grad) <= TOL
     assert torch.equal(rd.grad.cpu(), go)
     # no residual, no activation (the plain module call of the reference)

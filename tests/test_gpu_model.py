@@ -38,8 +38,6 @@ def test_model_matches_reference_golden(name):
     assert rel_err(out, fix["out"]) <= TOL
     loss = _loss(out, batch)
     assert rel_err(loss, fix["loss"]) <= TOL
-    if "ragged" in name:
-        return                       # forward honours the linspace quirk; backward of ragged batches is a documented gap
     loss.backward()
     # The golden gradients are themselves an fp32 evaluation (the reference's CPU path): |cuda - golden| is bounded by
     # the sum of both sides' rounding errors, so each gradient tensor gets 1e-5 plus the golden's own distance from the
