@@ -107,6 +107,22 @@ int stinet_edge_message_bwd_source(const float* P, int64_t ldp, const float* Q, 
                                    const int32_t* col_s, int64_t n_rows, int64_t hidden, float* dQ, int64_t lddq,
                                    stinet_stream_t stream);
 
+/* The same stage with the ReLU decisions saved for backward (hidden % 4 == 0, 16-byte aligned rows): forward also
+ * writes mask[e][chunk] (uint4 = 128 decision bits [P_i+Q_j > 0] of ORIGINAL edge e = eid_t[k] and 128-channel chunk;
+ * word `comp`, bit `lane` <-> channel chunk*128 + 4*lane + comp), n_edges * ceil(hidden/128) * 16 bytes.  The backward
+ * kernels read the masks instead of re-evaluating P_i + Q_j: dP needs no neighbour rows at all, dQ gathers dhid only.
+ * Results are bit-identical to the recomputing entry points above. */
+int stinet_edge_message_fwd_mask(const float* P, int64_t ldp, const float* Q, int64_t ldq, const int32_t* rowptr_t,
+                                 const int32_t* col_t, const int32_t* eid_t, int64_t n_rows, int64_t hidden,
+                                 float* hid, int64_t ldh, void* mask, stinet_stream_t stream);
+int stinet_edge_message_bwd_target_mask(const float* dhid, int64_t ldd, const int32_t* rowptr_t, const int32_t* eid_t,
+                                        const void* mask, int64_t n_rows, int64_t hidden, float* dP, int64_t lddp,
+                                        stinet_stream_t stream);
+int stinet_edge_message_bwd_source_mask(const float* dhid, int64_t ldd, const int32_t* rowptr_t,
+                                        const int32_t* rowptr_s, const int32_t* col_s, const int32_t* eid_s,
+                                        const void* mask, int64_t n_rows, int64_t hidden, float* dQ, int64_t lddq,
+                                        stinet_stream_t stream);
+
 /* Parameters of the hoisted first layer from nn.0's own W [hidden, kin] / b [hidden] (kin = 2*din, or din for
  * EdgeConvTransInv):  Wcat [2*hidden, din] = [Wa - Wb ; Wb]  (trans_inv: [-W ; W]),  bcat [2*hidden] = [b ; 0]
  * (b / bcat nullable together), and the matching gradient fold  dW = [dP-part | dQ-part - dP-part], db = dbcat[:hidden].

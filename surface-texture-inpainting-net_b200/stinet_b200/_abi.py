@@ -28,6 +28,9 @@ SIGNATURES = {
     "stinet_edge_message_fwd": (I, [P, I64, P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_target": (I, [P, I64, P, I64, P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_source": (I, [P, I64, P, I64, P, I64, P, P, P, I64, I64, P, I64, P]),
+    "stinet_edge_message_fwd_mask": (I, [P, I64, P, I64, P, P, P, I64, I64, P, I64, P, P]),
+    "stinet_edge_message_bwd_target_mask": (I, [P, I64, P, P, P, I64, I64, P, I64, P]),
+    "stinet_edge_message_bwd_source_mask": (I, [P, I64, P, P, P, P, P, I64, I64, P, I64, P]),
     "stinet_edgeconv_hoist_fwd": (I, [P, I64, P, I64, I64, I, P, P, P]),
     "stinet_edgeconv_hoist_bwd": (I, [P, P, I64, I64, I, P, I64, P, P]),
     "stinet_pool_max_fwd": (I, [P, I64, P, P, I64, I64, I64, P, I64, P, P]),
