@@ -68,6 +68,10 @@ size_t stinet_csr_workspace_bytes(int64_t n_rows, int64_t n_items);
 int stinet_csr_build(const int64_t* key, const int64_t* other, int64_t n_items, int64_t n_rows, int32_t* rowptr,
                      int32_t* perm, int32_t* col, int32_t* key32, int32_t* status, void* workspace,
                      size_t workspace_bytes, stinet_stream_t stream);
+/* tpos_s[k_s] = position in the by-target CSR of the edge at position k_s of the by-source CSR (eid_t / eid_s = the
+ * two `perm` outputs of stinet_csr_build over the same edge list); scratch: n_items int32. */
+int stinet_csr_cross_positions(const int32_t* eid_t, const int32_t* eid_s, int64_t n_items, int32_t* tpos_s,
+                               int32_t* scratch, stinet_stream_t stream);
 /* Block-diagonal batching of structures built once per sample (the offsets are those of
  * HierarchicalData.__inc__, utils/data_utils.py:29-42, which the reference applies to the COO tensors in collate):
  *   dst[dst_off[p] + i] = src[p][i] + add[p]   for i < len[p], p < n_parts.
@@ -108,18 +112,19 @@ int stinet_edge_message_bwd_source(const float* P, int64_t ldp, const float* Q, 
                                    stinet_stream_t stream);
 
 /* The same stage with the ReLU decisions saved for backward (hidden % 4 == 0, 16-byte aligned rows): forward also
- * writes mask[e][chunk] (uint4 = 128 decision bits [P_i+Q_j > 0] of ORIGINAL edge e = eid_t[k] and 128-channel chunk;
- * word `comp`, bit `lane` <-> channel chunk*128 + 4*lane + comp), n_edges * ceil(hidden/128) * 16 bytes.  The backward
- * kernels read the masks instead of re-evaluating P_i + Q_j: dP needs no neighbour rows at all, dQ gathers dhid only.
+ * writes mask[k * hidden/4 + c4] = one byte whose low nibble holds the decision bits [P_i+Q_j > 0] of channels
+ * 4*c4..4*c4+3 for the edge at POSITION k of the by-target CSR (n_edges * hidden/4 bytes, written and re-read as a
+ * stream).  The backward kernels read the masks instead of re-evaluating P_i + Q_j: dP needs no neighbour rows at
+ * all, dQ gathers dhid only; tpos_s[k_s] = by-target position of by-source entry k_s (stinet_csr_cross_positions).
  * Results are bit-identical to the recomputing entry points above. */
 int stinet_edge_message_fwd_mask(const float* P, int64_t ldp, const float* Q, int64_t ldq, const int32_t* rowptr_t,
-                                 const int32_t* col_t, const int32_t* eid_t, int64_t n_rows, int64_t hidden,
-                                 float* hid, int64_t ldh, void* mask, stinet_stream_t stream);
-int stinet_edge_message_bwd_target_mask(const float* dhid, int64_t ldd, const int32_t* rowptr_t, const int32_t* eid_t,
-                                        const void* mask, int64_t n_rows, int64_t hidden, float* dP, int64_t lddp,
+                                 const int32_t* col_t, int64_t n_rows, int64_t hidden, float* hid, int64_t ldh,
+                                 void* mask, stinet_stream_t stream);
+int stinet_edge_message_bwd_target_mask(const float* dhid, int64_t ldd, const int32_t* rowptr_t, const void* mask,
+                                        int64_t n_rows, int64_t hidden, float* dP, int64_t lddp,
                                         stinet_stream_t stream);
 int stinet_edge_message_bwd_source_mask(const float* dhid, int64_t ldd, const int32_t* rowptr_t,
-                                        const int32_t* rowptr_s, const int32_t* col_s, const int32_t* eid_s,
+                                        const int32_t* rowptr_s, const int32_t* col_s, const int32_t* tpos_s,
                                         const void* mask, int64_t n_rows, int64_t hidden, float* dQ, int64_t lddq,
                                         stinet_stream_t stream);
 

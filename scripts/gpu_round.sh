@@ -27,11 +27,11 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
 # full capture of the dominant kernels, eager launches: pass 1 = start of forward (level 0/1 shapes), pass 2 = start of
 # backward (output blocks on level 0 come first)
 timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:'edge_message_fwd|pool_max_fwd|seg_colreduce|segnorm_apply|segnorm_fused_fwd|segnorm_slice_apply|row_gather|gemm_tc' -c ${NCU_COUNT:-24} \
+  -k regex:'edge_message_fwd|pool_max_fwd|seg_colreduce|segnorm_apply|segnorm_fused_fwd|segnorm_slice_apply|row_gather|gemm_tc|csr_' -c ${NCU_COUNT:-24} \
   -o $OUT/prof_fwd_$TAG -f python bench.py --steps 1 --warmup 3 --no-e2e --no-profile --no-cpu-baseline --no-graph \
   --profiler-range > $OUT/ncu_full_fwd_$TAG.log 2>&1; echo "ncu full fwd exit $?"
 timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  --kernel-name-base demangled -k regex:"bwd|colsum_partial|cluster_sum|gemm_tc_kernel<128, 0, 1|gemm_tc_kernel<128, 1, 1" -c ${NCU_COUNT:-24} \
+  --kernel-name-base mangled -k regex:"bwd|colsum_partial|cluster_sum|splitk_reduce|gemm_tc_kernelILi128ELb0ELb1|gemm_tc_kernelILi128ELb1ELb1" -c ${NCU_COUNT:-24} \
   -o $OUT/prof_bwd_$TAG -f python bench.py --steps 1 --warmup 3 --no-e2e --no-profile --no-cpu-baseline --no-graph \
   --profiler-range > $OUT/ncu_full_bwd_$TAG.log 2>&1; echo "ncu full bwd exit $?"
 for f in fwd bwd; do

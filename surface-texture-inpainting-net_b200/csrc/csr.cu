@@ -181,6 +181,18 @@ __global__ void csr_gather_col(const int64_t* __restrict__ other, const int32_t*
   }
 }
 
+// tpos_s[k_s] = position, in the by-target CSR, of the edge that sits at position k_s of the by-source CSR
+// (both are permutations of the same original edge ids): inv[eid_t[k]] = k, then tpos_s[k_s] = inv[eid_s[k_s]].
+__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    inv[perm[k]] = (int32_t)k;
+}
+__global__ void gather_i32_kernel(const int32_t* __restrict__ table, const int32_t* __restrict__ idx, int64_t n,
+                                  int32_t* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    out[k] = table[idx[k]];
+}
+
 // Block-diagonal batching of per-sample structures: part p of the destination is src[p][0..len) + add[p].
 // Up to kConcatParts parts travel by value in the launch parameters (no device-side pointer table, no H2D copy).
 constexpr int kConcatParts = 32;
@@ -304,4 +316,16 @@ extern "C" int stinet_concat_i32(const int32_t* const* src, const int64_t* len, 
     K(concat_i32_kernel<<<grid, 256, 0, stream>>>(a, dst));
   }
   return check_launch("concat_i32");
+}
+
+extern "C" int stinet_csr_cross_positions(const int32_t* eid_t, const int32_t* eid_s, int64_t n_items, int32_t* tpos_s,
+                                          int32_t* scratch, stinet_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(n_items >= 0, STINET_ERR_ARG, "csr_cross_positions: negative size");
+  if (n_items == 0) return STINET_OK;
+  STINET_REQUIRE(eid_t && eid_s && tpos_s && scratch, STINET_ERR_ARG, "csr_cross_positions: null pointer");
+  const int grid = wave_grid(n_items, 256 * 4, 8);
+  K(invert_perm_kernel<<<grid, 256, 0, stream>>>(eid_t, n_items, scratch));
+  K(gather_i32_kernel<<<grid, 256, 0, stream>>>(scratch, eid_s, n_items, tpos_s));
+  return check_launch("csr_cross_positions");
 }

@@ -402,9 +402,12 @@ static bool is_bf16_mode(int mode) { return mode == tc::MODE_BF16 || mode == tc:
 
 // fp32 mode, C[I,J] over T: split the operands in HBM first (MODE_TF32X3P) when the GEMM is compute-heavy enough that
 // the in-kernel split (shared-memory bandwidth) is the limiter and the two extra HBM passes are cheap next to it:
-// flops per operand byte = I*J / (2*(I+J)) above a threshold (STINET_TC_PRESPLIT overrides it; 0 disables).
+// flops per operand byte = I*J / (2*(I+J)) above the threshold STINET_TC_PRESPLIT (unset or 0: disabled).
 static bool tc_presplit(int precision, int64_t I, int64_t J, int64_t T) {
-  static const int thr = [] { const char* e = getenv("STINET_TC_PRESPLIT"); return e ? atoi(e) : 160; }();
+  // Measured on B200 (scripts/presplit_ab.sh, profiles/r1_h_gemm.md): the kernel itself runs 1.3-1.4x faster on planes,
+  // but the two split passes per call eat most of it (fwd 4096x1024 +13 %, wgrad -6 %), so the mode is OFF unless asked
+  // for; it pays once the planes are produced by the operand's producer or cached across fwd / dgrad / wgrad.
+  static const int thr = [] { const char* e = getenv("STINET_TC_PRESPLIT"); return e ? atoi(e) : 0; }();
   if (precision != STINET_PREC_FP32 || thr <= 0) return false;
   if ((I | J | T) & 3) return false;                       // packed planes must keep 16-byte row pitches
   return I * J >= (int64_t)thr * 2 * (I + J) && T >= 256;

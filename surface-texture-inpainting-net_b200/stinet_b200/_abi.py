@@ -22,14 +22,15 @@ SIGNATURES = {
     "stinet_launch_count": (ctypes.c_longlong, []),
     "stinet_csr_workspace_bytes": (SZ, [I64, I64]),
     "stinet_csr_build": (I, [P, P, I64, I64, P, P, P, P, P, P, SZ, P]),
+    "stinet_csr_cross_positions": (I, [P, P, I64, P, P, P]),
     "stinet_concat_i32": (I, [P, P, P, P, I, P, P]),
     "stinet_aggregate_fwd": (I, [P, I64, P, P, P, I64, I64, I64, I, P, I64, P, P]),
     "stinet_aggregate_bwd": (I, [P, I64, P, P, P, P, P, I64, I64, I, P, I64, P]),
     "stinet_edge_message_fwd": (I, [P, I64, P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_target": (I, [P, I64, P, I64, P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_source": (I, [P, I64, P, I64, P, I64, P, P, P, I64, I64, P, I64, P]),
-    "stinet_edge_message_fwd_mask": (I, [P, I64, P, I64, P, P, P, I64, I64, P, I64, P, P]),
-    "stinet_edge_message_bwd_target_mask": (I, [P, I64, P, P, P, I64, I64, P, I64, P]),
+    "stinet_edge_message_fwd_mask": (I, [P, I64, P, I64, P, P, I64, I64, P, I64, P, P]),
+    "stinet_edge_message_bwd_target_mask": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_edge_message_bwd_source_mask": (I, [P, I64, P, P, P, P, P, I64, I64, P, I64, P]),
     "stinet_edgeconv_hoist_fwd": (I, [P, I64, P, I64, I64, I, P, P, P]),
     "stinet_edgeconv_hoist_bwd": (I, [P, P, I64, I64, I, P, I64, P, P]),

@@ -60,16 +60,29 @@ class EdgeCSR:
         # by target: row i lists its in-edges in original order; col_t = source vertex, eid_t = original edge id
         self.rowptr_t, self.eid_t, self.col_t, _ = build_csr(self._dst, self._src, self.n, status=status)
         self._by_source = None
+        self._tpos_s = None
 
     @classmethod
-    def from_arrays(cls, n: int, rowptr_t, col_t, eid_t, rowptr_s, col_s, eid_s) -> "EdgeCSR":
+    def from_arrays(cls, n: int, rowptr_t, col_t, eid_t, rowptr_s, col_s, eid_s, tpos_s=None) -> "EdgeCSR":
         """Wrap arrays that already exist (stinet_b200.structure: built once per sample, concatenated per batch)."""
         self = cls.__new__(cls)
         self.n, self.e = int(n), int(col_t.numel())
         self._src = self._dst = self._status = None
         self.rowptr_t, self.col_t, self.eid_t = rowptr_t, col_t, eid_t
         self._by_source = (rowptr_s, col_s, eid_s)
+        self._tpos_s = tpos_s
         return self
+
+    def tpos_s(self) -> torch.Tensor:
+        """By-target position of every by-source entry (where the saved ReLU masks of an out-edge live)."""
+        if getattr(self, "_tpos_s", None) is None:
+            _, _, eid_s = self.by_source()
+            out = torch.empty(max(self.e, 1), dtype=torch.int32, device=self.rowptr_t.device)
+            scratch = torch.empty(max(self.e, 1), dtype=torch.int32, device=self.rowptr_t.device)
+            _abi.call("stinet_csr_cross_positions", self.eid_t.data_ptr(), eid_s.data_ptr(), self.e, out.data_ptr(),
+                      scratch.data_ptr(), _stream(), cost=(16 * self.e, 0, ""))
+            self._tpos_s = out
+        return self._tpos_s
 
     def by_source(self):
         """rowptr_s, col_s (= target vertex of each out-edge), eid_s -- only needed by backward passes."""

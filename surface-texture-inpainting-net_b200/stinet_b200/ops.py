@@ -116,8 +116,8 @@ def linear(x, weight, bias=None, rowmask=None, precision="fp32"):
 class EdgeMessageFn(Function):
     """hid[i] = mean_{j->i} relu(P[i] + Q[j]),  PQ = [P | Q] of shape [N, 2H].
 
-    Main path (H % 4 == 0, aligned rows): forward saves the ReLU decisions as bit masks (16 bytes per edge and 128
-    channels) and backward reads those instead of P and Q -- dP becomes a row-local count, dQ gathers one row per
+    Main path (H % 4 == 0, aligned rows): forward saves the ReLU decisions (one byte per edge and float4 column) and
+    backward reads those instead of P and Q -- dP becomes a row-local count, dQ gathers one row per
     out-edge instead of two, and [P|Q] itself does not have to be kept for this op.  Odd widths recompute P_i + Q_j."""
 
     @staticmethod
@@ -132,12 +132,10 @@ class EdgeMessageFn(Function):
         ctx.shape = (n, h)
         ctx.masked = h % 4 == 0 and ld % 4 == 0 and pq.data_ptr() % 16 == 0
         if ctx.masked:
-            nchunk = (h + 127) // 128
-            mask = torch.empty((max(csr.e, 1), nchunk, 4), dtype=torch.int32, device=pq.device)
+            mask = torch.empty((max(csr.e, 1), h // 4), dtype=torch.uint8, device=pq.device)
             _abi.call("stinet_edge_message_fwd_mask", pq.data_ptr(), ld, pq.data_ptr() + 4 * h, ld,
-                      csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), csr.eid_t.data_ptr(), n, h, hid.data_ptr(), h,
-                      mask.data_ptr(), _stream(),
-                      cost=(csr.e * (4 * h + 8 + 16 * nchunk) + n * (8 * h + 4), 2 * csr.e * h, f"H{h}"))
+                      csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h, hid.data_ptr(), h, mask.data_ptr(), _stream(),
+                      cost=(csr.e * (4 * h + 4 + h // 4) + n * (8 * h + 4), 2 * csr.e * h, f"H{h}"))
             ctx.save_for_backward(mask)
             return hid
         _abi.call("stinet_edge_message_fwd", pq.data_ptr(), ld, pq.data_ptr() + 4 * h, ld, csr.rowptr_t.data_ptr(),
@@ -160,14 +158,14 @@ class EdgeMessageFn(Function):
             if _ld(dhid) % 4 or dhid.data_ptr() % 16:
                 dhid = dhid.contiguous().clone()         # a fresh allocation is 16-byte aligned
             (mask,) = ctx.saved_tensors
-            nchunk = mask.shape[1]
+            tpos_s = csr.tpos_s()
             _abi.call("stinet_edge_message_bwd_target_mask", dhid.data_ptr(), _ld(dhid), csr.rowptr_t.data_ptr(),
-                      csr.eid_t.data_ptr(), mask.data_ptr(), n, h, dpq.data_ptr(), h2, s,
-                      cost=(csr.e * (16 * nchunk + 4) + n * (8 * h + 4), csr.e * h, f"H{h}"))
+                      mask.data_ptr(), n, h, dpq.data_ptr(), h2, s,
+                      cost=(csr.e * (h // 4) + n * (8 * h + 4), csr.e * h, f"H{h}"))
             _abi.call("stinet_edge_message_bwd_source_mask", dhid.data_ptr(), _ld(dhid), csr.rowptr_t.data_ptr(),
-                      rowptr_s.data_ptr(), col_s.data_ptr(), eid_s.data_ptr(), mask.data_ptr(), n, h,
+                      rowptr_s.data_ptr(), col_s.data_ptr(), tpos_s.data_ptr(), mask.data_ptr(), n, h,
                       dpq.data_ptr() + 4 * h, h2, s,
-                      cost=(csr.e * (4 * h + 16 * nchunk + 12) + n * (4 * h + 4), csr.e * h, f"H{h}"))
+                      cost=(csr.e * (4 * h + h // 4 + 12) + n * (4 * h + 4), csr.e * h, f"H{h}"))
             return dpq, None
         (pq,) = ctx.saved_tensors
         ld = _ld(pq)

@@ -35,7 +35,7 @@ from . import _abi
 from .graph import ClusterCSR, EdgeCSR, _stream
 
 _EDGE_KEY = re.compile(r"^(edge_index|hierarchy_edge_index_(\d+)|hierarchy_dil_\d+_edge_index_(\d+))$")
-_EDGE_ARRAYS = ("rowptr_t", "col_t", "eid_t", "rowptr_s", "col_s", "eid_s")
+_EDGE_ARRAYS = ("rowptr_t", "col_t", "eid_t", "rowptr_s", "col_s", "eid_s", "tpos_s")
 _CLUSTER_ARRAYS = ("rowptr", "member", "trace32")
 
 
@@ -71,7 +71,7 @@ class SampleStructure:
             csr = EdgeCSR(ei, nv[lvl])
             rowptr_s, col_s, eid_s = csr.by_source()
             st.edges[key] = dict(rowptr_t=csr.rowptr_t, col_t=csr.col_t, eid_t=csr.eid_t, rowptr_s=rowptr_s,
-                                 col_s=col_s, eid_s=eid_s)
+                                 col_s=col_s, eid_s=eid_s, tpos_s=csr.tpos_s()[:csr.e])
             st.n_edges[key] = csr.e
         for lvl in range(1, n_levels + 1):
             tr = sample[f"hierarchy_trace_index_{lvl}"].to(device)
@@ -125,7 +125,7 @@ def batch_structure(structs: Sequence[SampleStructure], device) -> Dict[str, tor
                 t = _concat(parts, rows, voff[lvl][:B], eoff[:B], voff[lvl][B] + 1, device)
             elif name.startswith("col"):
                 t = _concat(parts, ne, eoff[:B], voff[lvl][:B], eoff[B], device)
-            else:                                                                  # eid: position in the collated edge list
+            else:                                                    # eid / tpos: positions in the collated edge list
                 t = _concat(parts, ne, eoff[:B], eoff[:B], eoff[B], device)
             out[f"csr:{key}:{name}"] = t
     for lvl in structs[0].clusters:

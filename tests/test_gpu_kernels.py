@@ -324,29 +324,30 @@ def test_edge_message_mask_kernels_equal_recomputing_kernels(kind, h):
         pq[1, :h] = -pq[2, h:]                      # exact zeros of P_i + Q_j: the decision is `> 0`, ties are off
     dh = torch.randn(n, h, generator=g).to(DEV)
     P, Q, ld = pq.data_ptr(), pq.data_ptr() + 4 * h, 2 * h
-    nchunk = (h + 127) // 128
     hid0, hid1 = torch.empty(n, h, device=DEV), torch.full((n, h), float("nan"), device=DEV)
     d0, d1 = torch.empty(n, 2 * h, device=DEV), torch.full((n, 2 * h), float("nan"), device=DEV)
-    mask = torch.zeros(max(csr.e, 1), nchunk, 4, dtype=torch.int32, device=DEV)
+    mask = torch.zeros(max(csr.e, 1), h // 4, dtype=torch.uint8, device=DEV)
     s = _stream()
     _abi.call("stinet_edge_message_fwd", P, ld, Q, ld, csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h,
               hid0.data_ptr(), h, s)
-    _abi.call("stinet_edge_message_fwd_mask", P, ld, Q, ld, csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(),
-              csr.eid_t.data_ptr(), n, h, hid1.data_ptr(), h, mask.data_ptr(), s)
+    _abi.call("stinet_edge_message_fwd_mask", P, ld, Q, ld, csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h,
+              hid1.data_ptr(), h, mask.data_ptr(), s)
     assert torch.equal(hid0, hid1)
-    # the masks are exactly the decisions, in ORIGINAL edge order
+    # the masks are exactly the decisions, in by-target CSR order
+    tpos = csr.tpos_s()
     if csr.e:
-        dec = (pq[ei[1].to(DEV), :h] + pq[ei[0].to(DEV), h:]) > 0                  # [E, h]
+        perm = csr.eid_t.long()
+        assert torch.equal(perm[tpos[:csr.e].long()], es.long())                   # tpos_s: by-source entry -> by-target slot
+        dec = (pq[ei[1].to(DEV)[perm], :h] + pq[ei[0].to(DEV)[perm], h:]) > 0      # [E, h]
         c = torch.arange(h, device=DEV)
-        chunk, lane, comp = c // 128, (c % 128) // 4, c % 4
-        bits = (mask[:, chunk, comp] >> lane) & 1
+        bits = (mask[:csr.e, c // 4].int() >> (c % 4)) & 1
         assert torch.equal(bits.bool(), dec)
     _abi.call("stinet_edge_message_bwd_target", P, ld, Q, ld, dh.data_ptr(), h, csr.rowptr_t.data_ptr(),
               csr.col_t.data_ptr(), n, h, d0.data_ptr(), 2 * h, s)
     _abi.call("stinet_edge_message_bwd_source", P, ld, Q, ld, dh.data_ptr(), h, csr.rowptr_t.data_ptr(), rs.data_ptr(),
               cs.data_ptr(), n, h, d0.data_ptr() + 4 * h, 2 * h, s)
-    _abi.call("stinet_edge_message_bwd_target_mask", dh.data_ptr(), h, csr.rowptr_t.data_ptr(), csr.eid_t.data_ptr(),
-              mask.data_ptr(), n, h, d1.data_ptr(), 2 * h, s)
+    _abi.call("stinet_edge_message_bwd_target_mask", dh.data_ptr(), h, csr.rowptr_t.data_ptr(), mask.data_ptr(), n, h,
+              d1.data_ptr(), 2 * h, s)
     _abi.call("stinet_edge_message_bwd_source_mask", dh.data_ptr(), h, csr.rowptr_t.data_ptr(), rs.data_ptr(),
-              cs.data_ptr(), es.data_ptr(), mask.data_ptr(), n, h, d1.data_ptr() + 4 * h, 2 * h, s)
+              cs.data_ptr(), tpos.data_ptr(), mask.data_ptr(), n, h, d1.data_ptr() + 4 * h, 2 * h, s)
     assert torch.equal(d0, d1)

@@ -41,6 +41,7 @@ def test_concatenated_structure_is_bit_identical(ragged):
         for x, y, name in zip(a.by_source(), b.by_source(), ("rowptr_s", "col_s", "eid_s")):
             assert torch.equal(x, y), (key, name)
         assert torch.equal(a.degree, b.degree)
+        assert torch.equal(a.tpos_s()[:a.e], b.tpos_s()[:b.e])
     for lvl in (1, 2):
         a, b = ref.cluster(lvl), got.cluster(lvl)
         assert (a.n_fine, a.n_coarse) == (b.n_fine, b.n_coarse)
