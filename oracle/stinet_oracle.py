@@ -454,3 +454,104 @@ def psnr(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0, mask: Option
     y = y / data_range
     mse = torch.mean((x - y) ** 2, dim=[0, 1])
     return -10 * torch.log10(mse + 1e-8)
+
+
+# ------------------------------------------------------------------------------------------------
+# SingleConvMeshNet (models/singleconvmeshnet.py:10-156): EdgeConv with BatchNorm1d over EDGES inside
+# the message MLP (edge_conv_filter.py:34-44), mean / max trace pooling without dim_size (:112-118), unpool + skip
+# concat (:140-141), checkpointed blocks (:129-131, :146-148 -- their BatchNorm buffers are updated twice per step).
+
+
+def _mlp_with_norm(k: int, dout: int) -> nn.Sequential:
+    """edge_conv_filter.py:34-44: Lin(k, 2*dout, no bias), BN1d, ReLU, Lin(2*dout, dout, no bias), BN1d"""
+    return nn.Sequential(nn.Linear(k, 2 * dout, bias=False), nn.BatchNorm1d(2 * dout), nn.ReLU(),
+                         nn.Linear(2 * dout, dout, bias=False), nn.BatchNorm1d(dout))
+
+
+class _NormEdgeFilter(nn.Module):
+    def __init__(self, din, dout, trans_inv=False, aggr="mean"):
+        super().__init__()
+        self.nn = _mlp_with_norm(din if trans_inv else 2 * din, dout)
+        self.trans_inv, self.aggr = trans_inv, aggr
+
+    def forward(self, x, edge_index):
+        return edge_conv(x, edge_index, self.nn, self.aggr, self.trans_inv)
+
+
+class _ResBlock(nn.Module):
+    """singleconvmeshnet.py:95-110 (the in-place `+=` of :107 is written out of place: with more than one filter the
+    reference's own backward raises, so only num_propagation_steps == 1 is reachable in training)."""
+
+    def __init__(self, filters):
+        super().__init__()
+        self.filters = nn.ModuleList(filters)
+
+    def forward(self, x, edge_index):
+        x = F.relu(self.filters[0](x, edge_index))
+        for f in list(self.filters)[1:]:
+            x = F.relu(x + f(x, edge_index))
+        return x
+
+
+class OracleSingleConvMeshNet(nn.Module):
+    def __init__(self, feature_number, num_propagation_steps, filter_sizes, num_classes=3, pooling_method="mean",
+                 aggr="mean"):
+        super().__init__()
+        self._pooling_method = pooling_method
+        self._graph_levels = len(filter_sizes)
+        left, right = [], []
+        curr = feature_number
+        for level, size in enumerate(filter_sizes):
+            filters = [_NormEdgeFilter(curr, size, trans_inv=(level == 0), aggr=aggr)]                # :44-51
+            filters += [_NormEdgeFilter(size, size, aggr=aggr) for _ in range(num_propagation_steps - 1)]
+            if level < len(filter_sizes) - 1:
+                fused = size + filter_sizes[level + 1]                                               # :58
+                rf = [_NormEdgeFilter(fused, size, aggr=aggr)]
+                rf += [_NormEdgeFilter(size, size, aggr=aggr) for _ in range(num_propagation_steps - 1)]
+                right.append(_ResBlock(rf))
+            left.append(_ResBlock(filters))
+            curr = size
+        # registration order of the reference (:88-90): left, right, final
+        self.left_geo_cnns = nn.ModuleList(left)
+        self.right_geo_cnns = nn.ModuleList(right)
+        f0 = filter_sizes[0]
+        self.final_convs = nn.ModuleList([nn.Sequential(nn.Linear(f0, f0 // 2), nn.BatchNorm1d(f0 // 2), nn.ReLU(),
+                                                        nn.Linear(f0 // 2, num_classes))])
+
+    def _pooling(self, x, trace):
+        n = int(trace.max()) + 1                                    # scatter_* without dim_size (:112-116)
+        if self._pooling_method == "mean":
+            return scatter_mean(x, trace, n)
+        if self._pooling_method == "max":
+            return scatter_max(x, trace, n)[0]
+        raise ValueError(self._pooling_method)
+
+    def forward(self, sample, double_update_checkpointed: bool = True):
+        """double_update_checkpointed: the reference wraps every block except the level-0 ones in
+        torch.utils.checkpoint (reentrant), so in training their forward runs twice per step and their BatchNorm
+        running statistics receive two momentum updates; here the block is simply evaluated a second time without
+        grad when the module is training."""
+        from torch.utils import checkpoint as _cp
+        G = self._graph_levels
+
+        def run(block, x, edges, checkpointed):
+            if checkpointed and self.training and double_update_checkpointed and torch.is_grad_enabled():
+                return _cp.checkpoint(block, x, edges, use_reentrant=True, preserve_rng_state=False)
+            return block(x, edges)
+
+        levels = [self.left_geo_cnns[0](sample.x, sample.edge_index)]                                 # :123
+        for level in range(1, G):                                                                     # :128-134
+            cur = self._pooling(levels[-1], sample[f"hierarchy_trace_index_{level}"])
+            levels.append(run(self.left_geo_cnns[level], cur, sample[f"hierarchy_edge_index_{level}"], True))
+        current = levels[-1]
+        for level in range(1, G):                                                                     # :139-149
+            back = current[sample[f"hierarchy_trace_index_{G - level}"]]
+            fused = torch.cat((levels[-(level + 1)], back), -1)
+            if level == G - 1:
+                current = self.right_geo_cnns[-level](fused, sample.edge_index)
+            else:
+                current = run(self.right_geo_cnns[-level], fused, sample[f"hierarchy_edge_index_{G - level - 1}"], True)
+        result = current
+        for conv in self.final_convs:
+            result = conv(result)
+        return result

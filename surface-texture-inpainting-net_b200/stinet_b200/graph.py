@@ -73,6 +73,20 @@ class EdgeCSR:
         self._tpos_s = tpos_s
         return self
 
+    def edge_clusters(self):
+        """(by_target, by_source): the EDGES (original order) as the fine side of two cluster maps onto their end points --
+        lets the row-gather / segmented-add kernels of pooling serve the literal per-edge message path
+        (x_i = unpool(x, by_target), x_j = unpool(x, by_source), mean over in-edges = pool_mean(msg, by_target))."""
+        if getattr(self, "_edge_clusters", None) is None:
+            if self._dst is None:
+                raise _abi.StinetError("the literal per-edge path needs an EdgeCSR built from edge_index (COO), not from "
+                                       "prebuilt arrays")
+            rowptr_s, _, eid_s = self.by_source()
+            self._edge_clusters = (
+                ClusterCSR.from_arrays(self.e, self.n, self.rowptr_t, self.eid_t, self._dst.to(torch.int32)),
+                ClusterCSR.from_arrays(self.e, self.n, rowptr_s, eid_s, self._src.to(torch.int32)))
+        return self._edge_clusters
+
     def tpos_s(self) -> torch.Tensor:
         """By-target position of every by-source entry (where the saved ReLU masks of an out-edge live)."""
         if getattr(self, "_tpos_s", None) is None:

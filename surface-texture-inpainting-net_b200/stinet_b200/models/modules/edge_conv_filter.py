@@ -6,6 +6,12 @@ The arithmetic is evaluated in the hoisted, segmented form on sm_100a kernels (S
     hid_i = mean_{j->i} relu(P_i + Q_j)                                                      (stinet_edge_message_*)
     out_i = hid_i W2^T + b2 * [deg_i > 0]                                                    (vertex GEMM)
 which equals mean_{j->i} nn([x_i || x_j - x_i]) of PyG's EdgeConv(aggr='mean'), including 0 for isolated vertices.
+
+`with_norm=True` (reference :34-44, used by SingleConvMeshNet: BatchNorm1d over the EDGES between the two Linears and
+after the second one) cannot be hoisted -- the statistics are taken over per-edge activations -- so that variant is
+evaluated literally on [E, .] matrices: x_i / x_j row gathers (stinet_unpool_*, the edges being the "fine" side of a
+cluster map onto their end points), the Linears as tcgen05 GEMMs over E rows, BatchNorm1d / ReLU as device tensor ops,
+and the mean over in-edges as stinet_pool_mean_* (deterministic segmented sums both ways, no atomics).
 """
 from __future__ import annotations
 
@@ -27,10 +33,12 @@ class EdgeConv(torch.nn.Module):
             raise NotImplementedError(
                 f"EdgeConv(aggr={aggr!r}): only the reference's 'mean' aggregation (edge_conv_filter.py:11) is fused; "
                 "use stinet_b200.ops.aggregate for add/max over explicit messages")
-        if not (isinstance(nn, Seq) and len(nn) == 3 and isinstance(nn[0], Lin) and isinstance(nn[2], Lin)
-                and isinstance(nn[1], torch.nn.ReLU)):
-            raise NotImplementedError("EdgeConv expects nn = Sequential(Linear, ReLU, Linear) (edge_conv_filter.py:46-55); "
-                                      "the with_norm=True variant (:34-44) is not part of the STINet path")
+        if not isinstance(nn, Seq):
+            raise NotImplementedError("EdgeConv expects nn = torch.nn.Sequential (edge_conv_filter.py:34-55)")
+        # Sequential(Linear, ReLU, Linear) is evaluated in the hoisted form; anything else (the with_norm variant)
+        # literally, per edge
+        self.hoistable = (len(nn) == 3 and isinstance(nn[0], Lin) and isinstance(nn[2], Lin)
+                          and isinstance(nn[1], torch.nn.ReLU))
         self.nn = nn
         self.aggr = self._aggr = aggr
         self.precision = "fp32"
@@ -40,8 +48,24 @@ class EdgeConv(torch.nn.Module):
         # trans_inv: nn.0(x_j - x_i) = (-W) x_i + W x_j;  else nn.0([x_i || x_j - x_i]) = (Wa - Wb) x_i + Wb x_j
         return ops.edgeconv_hoist(self.nn[0].weight, self.nn[0].bias, self.trans_inv)
 
+    def literal_forward(self, x, csr):
+        """mean_{j->i} nn([x_i || x_j - x_i]) with nn applied to the [E, .] message matrix (PyG's own order of
+        evaluation); rows of the message matrix are in ORIGINAL edge order."""
+        by_target, by_source = csr.edge_clusters()
+        x_i = ops.unpool(x, by_target)
+        x_j = ops.unpool(x, by_source)
+        m = (x_j - x_i) if self.trans_inv else torch.cat([x_i, x_j - x_i], dim=-1)
+        for layer in self.nn:
+            if isinstance(layer, Lin):
+                m = ops.linear(m, layer.weight, layer.bias, None, self.precision)
+            else:
+                m = layer(m)
+        return ops.pool_mean(m, by_target)
+
     def forward(self, x, edge_index):
         csr = as_edge_csr(edge_index, x.shape[0])
+        if not self.hoistable:
+            return self.literal_forward(x, csr)
         wcat, bcat = self.hoisted_first_layer()
         pq = ops.linear(x, wcat, bcat, None, self.precision)
         hid = ops.edge_message(pq, csr)
@@ -61,8 +85,15 @@ def get_gcn_filter(input_size: int, output_size, activation: torch.nn.Module = t
     if module is None:
         module = EdgeConv
     if with_norm:
-        raise NotImplementedError("with_norm=True (BatchNorm1d over edges, edge_conv_filter.py:34-44) is only used by "
-                                  "SingleConvMeshNet and is out of scope for the STINet hot path")
+        # reference :34-44 -- no biases, BatchNorm1d over the edge dimension after each Linear
+        inner_module = Seq(
+            Lin(double_input_size, 2 * output_size, bias=False),
+            torch.nn.BatchNorm1d(2 * output_size),
+            activation(inplace=inplace),
+            Lin(2 * output_size, output_size, bias=False),
+            torch.nn.BatchNorm1d(output_size),
+        )
+        return module(inner_module, aggr=aggregation)
     if activation is not torch.nn.ReLU:
         raise NotImplementedError("the fused message kernel implements the reference's ReLU (edge_conv_filter.py:10)")
     inner_module = Seq(

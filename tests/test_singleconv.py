@@ -1,0 +1,110 @@
+"""SingleConvMeshNet on the CPU: the oracle restatement against golden vectors minted from the
+reference's own models/singleconvmeshnet.py (tests/golden/make_golden_singleconv.py), and the HOST LOGIC of the
+product module -- schedule, checkpointing / BatchNorm double update, edge-as-cluster index plumbing, state_dict
+layout -- against the same vectors with the CUDA entry points replaced by plain-torch stand-ins.  The stand-ins exist
+only inside this test (the product has no CPU path); the kernels themselves are checked on the B200
+(tests/test_gpu_kernels.py per kernel, tests/test_gpu_zz_singleconv.py for this network)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, assert_grads_close, rel_err
+from oracle import stinet_oracle as O
+
+FIXTURES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "singleconv", "*.pt")))
+TOL = 1e-5
+
+
+def load(name):
+    from stinet_b200.data import GraphBatch
+    fix = torch.load(os.path.join(GOLDEN_DIR, "singleconv", f"{name}.pt"), weights_only=False)
+    fix["batch"] = GraphBatch(**fix["sample"])
+    return fix
+
+
+def check_against_golden(net, batch, fix):
+    batch.x = batch.x.clone().requires_grad_(True)
+    out = net(batch)
+    loss = out.square().mean()
+    loss.backward()
+    assert rel_err(out, fix["out"]) <= TOL and rel_err(loss, fix["loss"]) <= TOL
+    got = {k: p.grad for k, p in net.named_parameters()}
+    got["__x__"] = batch.x.grad
+    assert_grads_close(got, dict(fix["grads"], __x__=fix["grad_x"]), TOL)
+    # BatchNorm buffers after one training step (checkpointed blocks: two momentum updates).  The running mean of the
+    # translation-invariant first layer is structurally zero (sum over a symmetric edge set of W(x_j - x_i)): noise only
+    for k, v in net.named_buffers():
+        ref = fix["buffers_after"][k]
+        if ref.is_floating_point():
+            assert float((v.detach().cpu() - ref).abs().max()) <= TOL * max(float(ref.abs().max()), 1e-3), k
+        else:
+            assert torch.equal(v.cpu(), ref), k
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 2
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_matches_reference_golden(name):
+    fix = load(name)
+    net = O.OracleSingleConvMeshNet(**fix["kwargs"])
+    assert list(net.state_dict()) == list(fix["state_dict"])
+    net.load_state_dict(fix["state_dict"])
+    check_against_golden(net.train(), fix["batch"], fix)
+
+
+@pytest.fixture
+def torch_stand_ins(monkeypatch):
+    """Plain-torch stand-ins for the C-ABI calls this network makes (test harness only)."""
+    from stinet_b200 import graph, ops
+
+    def build_csr(key, other, n_rows, want_key32=False, status=None):
+        rowptr, perm = O.csr_by_key(key, n_rows)
+        col = other[perm.long()].to(torch.int32) if other is not None else None
+        return rowptr, perm, col, (key.to(torch.int32) if want_key32 else None)
+
+    def unpool(xc, cl):
+        return xc.index_select(0, cl.trace32.long())
+
+    def pool_mean(x, cl):
+        return O.scatter_mean(x, cl.trace32.long(), cl.n_coarse)
+
+    def pool_max(x, cl):
+        return O.scatter_max(x, cl.trace32.long(), cl.n_coarse)
+
+    def linear(x, w, b=None, rowmask=None, precision="fp32"):
+        assert rowmask is None
+        return torch.nn.functional.linear(x, w, b)
+
+    monkeypatch.setattr(graph, "build_csr", build_csr)
+    monkeypatch.setattr(graph, "_require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(ops, "unpool", unpool)
+    monkeypatch.setattr(ops, "pool_mean", pool_mean)
+    monkeypatch.setattr(ops, "pool_max", pool_max)
+    monkeypatch.setattr(ops, "linear", linear)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_host_logic_with_stand_in_kernels_matches_reference_golden(name, torch_stand_ins):
+    from stinet_b200.models.singleconvmeshnet import SingleConvMeshNet
+    fix = load(name)
+    net = SingleConvMeshNet(**fix["kwargs"])
+    assert list(net.state_dict()) == list(fix["state_dict"])
+    net.load_state_dict(fix["state_dict"], strict=True)
+    check_against_golden(net.train(), fix["batch"], fix)
+
+
+def test_edges_as_clusters_index_plumbing(torch_stand_ins):
+    """x_i / x_j gathers and the mean over in-edges expressed through the pooling structures: members of a target's
+    cluster are its in-edges in original order, trace32 is the end point of every original edge."""
+    from stinet_b200.graph import EdgeCSR
+    ei = torch.tensor([[0, 2, 1, 2, 3, 0], [1, 1, 0, 3, 3, 3]])
+    csr = EdgeCSR(ei, 5)
+    by_t, by_s = csr.edge_clusters()
+    assert (by_t.n_fine, by_t.n_coarse) == (6, 5)
+    assert by_t.trace32.tolist() == ei[1].tolist() and by_s.trace32.tolist() == ei[0].tolist()
+    assert by_t.rowptr.tolist() == [0, 1, 3, 3, 6, 6] and by_t.member.tolist() == [2, 0, 1, 3, 4, 5]
+    assert by_s.rowptr.tolist() == [0, 2, 3, 5, 6, 6] and by_s.member.tolist() == [0, 5, 2, 1, 3, 4]
