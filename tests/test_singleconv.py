@@ -3,7 +3,7 @@ reference's own models/singleconvmeshnet.py (tests/golden/make_golden_singleconv
 product module -- schedule, checkpointing / BatchNorm double update, edge-as-cluster index plumbing, state_dict
 layout -- against the same vectors with the CUDA entry points replaced by plain-torch stand-ins.  The stand-ins exist
 only inside this test (the product has no CPU path); the kernels themselves are checked on the B200
-(tests/test_gpu_kernels.py per kernel, tests/test_gpu_zz_singleconv.py for this network)."""
+(tests/test_gpu_kernels.py per kernel, tests/test_zz_gpu_singleconv.py for this network)."""
 import glob
 import os
 
