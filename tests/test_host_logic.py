@@ -114,3 +114,111 @@ def test_shipped_configs_param_counts():
     n2 = S.define_G(input_nc=4, output_nc=3, ngf=64, n_blocks=9, dilations=[1] * 9, norm="instance",
                     pooling_type="max", n_levels=2, filter_type="edgeconv", checkpoint_bottleneck=False)
     assert sum(p.numel() for p in n2.parameters()) == 4201411
+
+
+def test_ragged_instance_norm_backward_composite_matches_autograd():
+    """ops._ragged_norm_backward (plain tensor ops, device-agnostic) against autograd of the oracle's restatement of the
+    reference's linspace-slice statistics (fastinstancenorm.py:53-82), fp64, with and without the fused ELU."""
+    from types import SimpleNamespace
+    from oracle import stinet_oracle as O
+    from stinet_b200 import ops
+    torch.manual_seed(0)
+    counts = [500, 77, 323]
+    n, c = sum(counts), 5
+    x = torch.randn(n, c, dtype=torch.float64) * 3 + 1.5
+    go = torch.randn(n, c, dtype=torch.float64)
+    batch = torch.repeat_interleave(torch.arange(3), torch.tensor(counts))
+    sp = torch.linspace(0, n, 4, dtype=torch.int).tolist()
+    cnt = torch.tensor(counts, dtype=torch.float64).view(-1, 1)
+    mean = torch.stack([x[sp[i]:sp[i + 1]].sum(0) for i in range(3)]) / cnt
+    xc = x - mean[batch]
+    rstd = (torch.stack([xc[sp[i]:sp[i + 1]].pow(2).sum(0) for i in range(3)]) / cnt + 1e-5).rsqrt()
+    seg = SimpleNamespace(true_ptr=[0, 500, 577, 900], slice_ptr_host=sp, n_seg=3, gid=batch.int(), cnt=cnt.flatten())
+    for act in (0, 1):
+        xr = x.clone().requires_grad_(True)
+        y = O.fast_instance_norm(xr, batch)
+        (torch.nn.functional.elu(y) if act else y).backward(go)
+        dx = ops._ragged_norm_backward(x, go, mean, rstd, seg, act)
+        assert float((dx - xr.grad).abs().max() / xr.grad.abs().max()) < 1e-12
+
+
+def test_segments_carry_true_and_slice_boundaries():
+    from stinet_b200.graph import Segments
+    rag = Segments(10, [7, 3], torch.zeros(10, dtype=torch.int32), "cpu")
+    assert rag.true_ptr == [0, 7, 10] and rag.slice_ptr_host == [0, 5, 10] and not rag.consistent
+    one = Segments(9, None, None, "cpu")
+    assert one.true_ptr == [0, 9] and one.slice_ptr_host == [0, 9]
+
+
+def test_flat_views_pack_a_batch_into_one_buffer():
+    """engine._flat_views: every tensor of a batch as a 256-byte aligned view of one flat buffer (what lets a
+    prefetched batch move device-to-device with a single copy)."""
+    from stinet_b200.engine import _flat_views
+    items = [("x", torch.randn(7, 3)), ("edge_index", torch.arange(10).view(2, 5)), ("empty", torch.zeros(0, 4)),
+             ("m", torch.tensor([[1], [0], [1]], dtype=torch.int32))]
+    flat, views = _flat_views(items, "cpu")
+    v = views(flat)
+    offs = []
+    for k, t in items:
+        assert v[k].shape == t.shape and v[k].dtype == t.dtype
+        v[k].copy_(t)
+        if t.numel():                                   # an empty view has no storage address worth checking
+            offs.append(v[k].data_ptr() - flat.data_ptr())
+    assert all(o % 256 == 0 for o in offs) and offs == sorted(offs)
+    other = torch.empty_like(flat)
+    other.copy_(flat)                                   # ONE copy moves the whole batch
+    for k, t in items:
+        assert torch.equal(views(other)[k], t)
+
+
+def test_block_diagonal_structure_offsets_with_stand_in_kernels(monkeypatch):
+    """stinet_b200.structure: the per-array (length, destination offset, added offset) plan of the block-diagonal
+    batching, checked against the structure of the COLLATED batch (the reference's HierarchicalData offsets,
+    utils/data_utils.py:29-42).  The two C-ABI calls involved are replaced by plain-torch stand-ins inside this test
+    only; on the B200 tests/test_gpu_structure.py checks the real kernels bit for bit."""
+    from oracle import stinet_oracle as O
+    from stinet_b200 import graph, structure, synthetic
+    from stinet_b200.data import collate
+
+    def build_csr(key, other, n_rows, want_key32=False, status=None):
+        rowptr, perm = O.csr_by_key(key, n_rows)
+        col = other[perm.long()].to(torch.int32) if other is not None else None
+        return rowptr, perm, col, (key.to(torch.int32) if want_key32 else None)
+
+    def concat(parts, lens, dst_offs, adds, total, device):
+        out = torch.full((total,), -12345, dtype=torch.int32)
+        for p, n, o, a in zip(parts, lens, dst_offs, adds):
+            out[o:o + n] = p[:n] + a
+        assert not (out == -12345).any()                # every element written exactly by the plan
+        return out
+
+    def tpos(self):
+        _, _, eid_s = self.by_source()
+        inv = torch.empty(max(self.e, 1), dtype=torch.int32)
+        inv[self.eid_t.long()] = torch.arange(self.e, dtype=torch.int32)
+        return inv[eid_s.long()] if self.e else inv
+
+    monkeypatch.setattr(graph, "build_csr", build_csr)
+    monkeypatch.setattr(graph, "_require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(graph.EdgeCSR, "tpos_s", tpos)
+    monkeypatch.setattr(structure, "_concat", concat)
+    a = synthetic.make_samples("icosphere", 2, 2, seed=49, subdiv=2, mask_radius=2)
+    b = synthetic.make_samples("plane", 1, 2, seed=7, rows=9, cols=11, mask_radius=2)
+    samples = [a[0], b[0], a[1]]
+    L = 2
+    ref = graph.GraphCache(collate(samples), L)
+    structs = [structure.SampleStructure.build(s, L, "cpu") for s in samples]
+    lean = structure.attach_batch_structure(collate(samples, keep_index=False), structs, "cpu")
+    assert "edge_index" not in lean
+    got = graph.GraphCache(lean, L)
+    for key, lvl in (("edge_index", 0), ("hierarchy_edge_index_1", 1), ("hierarchy_edge_index_2", 2)):
+        x, y = ref.edges(key, lvl), got.edges(key, lvl)
+        for name in ("rowptr_t", "col_t", "eid_t"):
+            assert torch.equal(getattr(x, name), getattr(y, name)), (key, name)
+        for p, q in zip(x.by_source(), y.by_source()):
+            assert torch.equal(p, q)
+        assert torch.equal(x.tpos_s()[:x.e], y.tpos_s()[:y.e])
+    for lvl in (1, 2):
+        x, y = ref.cluster(lvl), got.cluster(lvl)
+        for name in ("rowptr", "member", "trace32"):
+            assert torch.equal(getattr(x, name), getattr(y, name)), (lvl, name)
