@@ -475,7 +475,20 @@ class _NormEdgeFilter(nn.Module):
         self.trans_inv, self.aggr = trans_inv, aggr
 
     def forward(self, x, edge_index):
-        return edge_conv(x, edge_index, self.nn, self.aggr, self.trans_inv)
+        dec = Decisions._active
+        if dec is None:
+            return edge_conv(x, edge_index, self.nn, self.aggr, self.trans_inv)
+        # same arithmetic with the ReLU's sign choices recorded or replayed (rows in original edge order)
+        x_j, x_i = x.index_select(0, edge_index[0]), x.index_select(0, edge_index[1])
+        m = (x_j - x_i) if self.trans_inv else torch.cat([x_i, x_j - x_i], dim=-1)
+        for layer in self.nn:
+            m = dec.relu(m) if isinstance(layer, nn.ReLU) else layer(m)
+        return aggregate(m, edge_index[1], x.size(0), self.aggr)
+
+
+def _relu(x):
+    dec = Decisions._active
+    return F.relu(x) if dec is None else dec.relu(x)
 
 
 class _ResBlock(nn.Module):
@@ -487,9 +500,9 @@ class _ResBlock(nn.Module):
         self.filters = nn.ModuleList(filters)
 
     def forward(self, x, edge_index):
-        x = F.relu(self.filters[0](x, edge_index))
+        x = _relu(self.filters[0](x, edge_index))
         for f in list(self.filters)[1:]:
-            x = F.relu(x + f(x, edge_index))
+            x = _relu(x + f(x, edge_index))
         return x
 
 
@@ -523,7 +536,8 @@ class OracleSingleConvMeshNet(nn.Module):
         if self._pooling_method == "mean":
             return scatter_mean(x, trace, n)
         if self._pooling_method == "max":
-            return scatter_max(x, trace, n)[0]
+            dec = Decisions._active
+            return (scatter_max(x, trace, n) if dec is None else dec.pool_max(x, trace, n))[0]
         raise ValueError(self._pooling_method)
 
     def forward(self, sample, double_update_checkpointed: bool = True):
@@ -553,5 +567,6 @@ class OracleSingleConvMeshNet(nn.Module):
                 current = run(self.right_geo_cnns[-level], fused, sample[f"hierarchy_edge_index_{G - level - 1}"], True)
         result = current
         for conv in self.final_convs:
-            result = conv(result)
+            for layer in conv:
+                result = _relu(result) if isinstance(layer, nn.ReLU) else layer(result)
         return result

@@ -108,3 +108,108 @@ def test_edges_as_clusters_index_plumbing(torch_stand_ins):
     assert by_t.trace32.tolist() == ei[1].tolist() and by_s.trace32.tolist() == ei[0].tolist()
     assert by_t.rowptr.tolist() == [0, 1, 3, 3, 6, 6] and by_t.member.tolist() == [2, 0, 1, 3, 4, 5]
     assert by_s.rowptr.tolist() == [0, 2, 3, 5, 6, 6] and by_s.member.tolist() == [0, 5, 2, 1, 3, 4]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# decision replay (oracle.Decisions) for SingleConvMeshNet: BatchNorm centres every pre-activation at zero, so on a real
+# mesh some ReLU sign (or max-pool winner) always sits within rounding distance of its discontinuity and two correct
+# fp32 evaluations differ on isolated gradient entries.  The fp64 oracle replays the choices of the implementation
+# under test and is then a smooth function of the same inputs: every gradient must agree within 1e-5, and every choice
+# that differs from the oracle's own must lie within DECISION_MARGIN of the discontinuity.
+
+DECISION_MARGIN = 2e-5
+
+
+def record_product_decisions(net, batch):
+    """One forward of the product module under no_grad (so no checkpoint recomputation: every block runs exactly once, in
+    schedule order) that records ("relu", bool mask) for every ReLU -- the nn.ReLU modules of the message MLPs and of the
+    head, the functional ReLU of the ResBlocks -- and ("pool", winners) for every max-pool.  BatchNorm buffers are put
+    back afterwards.  Deterministic kernels => the choices of the real training pass are the same."""
+    from stinet_b200 import ops
+    from stinet_b200.models.singleconvmeshnet import SingleConvMeshNet
+    choices, handles, patched = [], [], []
+    buffers = {k: v.detach().clone() for k, v in net.named_buffers()}
+
+    def relu_and_record(x, *a, **k):
+        choices.append(("relu", (x.detach() > 0).cpu()))
+        return torch.nn.functional.relu(x)
+
+    for m in net.modules():
+        if isinstance(m, torch.nn.ReLU):
+            handles.append(m.register_forward_pre_hook(lambda mod, inp: choices.append(("relu", (inp[0].detach() > 0).cpu()))))
+        if isinstance(m, SingleConvMeshNet.ResBlock):
+            patched.append((m, m._act))
+            m._act = relu_and_record
+    real_pool_max = ops.pool_max
+
+    def pool_max(x, cl):
+        out, arg = real_pool_max(x, cl)
+        choices.append(("pool", arg.detach().long().cpu()))
+        return out, arg
+
+    ops.pool_max = pool_max
+    try:
+        with torch.no_grad():
+            net(batch)
+    finally:
+        ops.pool_max = real_pool_max
+        for h in handles:
+            h.remove()
+        for m, act in patched:
+            m._act = act
+        with torch.no_grad():
+            for k, v in net.named_buffers():
+                v.copy_(buffers[k])
+    return choices
+
+
+def oracle_with_replayed_decisions(fix, choices, dtype=torch.float64):
+    import copy
+    orc = O.OracleSingleConvMeshNet(**fix["kwargs"])
+    orc.load_state_dict(fix["state_dict"])
+    orc = orc.to(dtype).train()
+    ob = copy.copy(fix["batch"])
+    ob.x = fix["batch"].x.detach().cpu().to(dtype).clone().requires_grad_(True)
+    with O.Decisions.replay(choices) as dec:
+        out = orc(ob, double_update_checkpointed=False)      # a recomputation would consume the stream twice
+        loss = out.square().mean()
+        loss.backward()
+    assert dec.pos == len(choices), "decision stream not fully consumed"
+    grads = {k: p.grad for k, p in orc.named_parameters()}
+    grads["__x__"] = ob.x.grad
+    return out.detach(), loss.detach(), grads, dec
+
+
+def check_against_replaying_oracle(net, batch, fix):
+    choices = record_product_decisions(net, batch)
+    batch.x = batch.x.detach().clone().requires_grad_(True)
+    out = net(batch)
+    loss = out.square().mean()
+    loss.backward()
+    t_out, t_loss, t_grads, dec = oracle_with_replayed_decisions(fix, choices)
+    assert dec.max_relu_margin <= DECISION_MARGIN and dec.max_pool_margin <= DECISION_MARGIN, \
+        (dec.n_relu_diff, dec.max_relu_margin, dec.n_pool_diff, dec.max_pool_margin)
+    assert rel_err(out, t_out) <= TOL and rel_err(loss, t_loss) <= TOL
+    got = {k: p.grad for k, p in net.named_parameters()}
+    got["__x__"] = batch.x.grad
+    assert_grads_close(got, t_grads, TOL)
+    return dec
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_decision_replay_protocol_with_stand_in_kernels(name, torch_stand_ins):
+    """The protocol itself, on the CPU: fp32 product module (stand-in kernels) against the fp64 oracle replaying its
+    choices -- the stream lines up call for call and every gradient agrees within 1e-5."""
+    from stinet_b200.models.singleconvmeshnet import SingleConvMeshNet
+    fix = load(name)
+    net = SingleConvMeshNet(**fix["kwargs"])
+    net.load_state_dict(fix["state_dict"], strict=True)
+    before = {k: v.clone() for k, v in net.named_buffers()}
+    choices = record_product_decisions(net.train(), fix["batch"])
+    assert all(torch.equal(v, before[k]) for k, v in net.named_buffers())        # recording leaves no trace
+    n_relu = sum(1 for k, _ in choices if k == "relu")
+    n_pool = sum(1 for k, _ in choices if k == "pool")
+    levels = len(fix["kwargs"]["filter_sizes"])
+    assert n_relu == 2 * (2 * levels - 1) + 1                                    # MLP + block ReLU per block, + the head
+    assert n_pool == (levels - 1 if fix["kwargs"]["pooling_method"] == "max" else 0)
+    check_against_replaying_oracle(net, fix["batch"], fix)

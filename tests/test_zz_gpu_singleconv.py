@@ -8,15 +8,16 @@ first tensor, the others are unknown).  A CPU emulation of that very wgrad with 
 split, truncating tensor-core accumulation, promotion every 128 elements) stays at 4e-7, so the dense layer is not the
 cause; the prime suspect is a discrete decision taken on the other side of a rounding-distance tie (ReLU sign right
 after a BatchNorm centres ~10^5 pre-activations at zero, or a max-pool winner) -- what the STINet tests neutralise with
-the decision-replay protocol (oracle.Decisions), not yet wired for this network.  The remaining checks could not be
+the decision-replay protocol (oracle.Decisions); it is wired for this network now (verified on the CPU with stand-in
+kernels) but has not met the hardware yet.  The remaining checks could not be
 run any more, so they are recorded as non-strict expectations instead of being asserted blind; the host logic of the
 whole network IS pinned to the golden vectors on the CPU (tests/test_singleconv.py).
-Next round: decision replay for SingleConvMeshNet, then make these strict."""
+Next round: run the decision-replay check below on the B200, then make these strict."""
 import pytest
 import torch
 
 from conftest import rel_err
-from test_singleconv import FIXTURES, check_against_golden, load
+from test_singleconv import FIXTURES, check_against_golden, check_against_replaying_oracle, load
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -57,6 +58,16 @@ def test_singleconv_forward_other_fixtures(name):
 def test_singleconv_gradients_and_buffers_match_reference_golden(name):
     fix = load(name)
     check_against_golden(_net(fix), fix["batch"].to(DEV), fix)
+
+
+@UNVERIFIED
+@pytest.mark.parametrize("name", FIXTURES)
+def test_singleconv_gradients_match_oracle_replaying_the_cuda_decisions(name):
+    """The decisive gradient check (protocol verified on the CPU in tests/test_singleconv.py): the fp64 oracle replays the
+    ReLU signs and max-pool winners the CUDA forward took; every gradient within 1e-5, every differing choice within
+    2e-5 of its discontinuity."""
+    fix = load(name)
+    check_against_replaying_oracle(_net(fix), fix["batch"].to(DEV), fix)
 
 
 @UNVERIFIED
