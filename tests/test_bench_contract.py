@@ -1,0 +1,49 @@
+"""bench.py's driver contract, as far as it can be exercised without a GPU: the reference arm (CPU oracle port) prints
+ONE JSON line with the keys the driver reads, and the GPU arm refuses to run without a device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+BENCH = os.path.join(ROOT, "bench.py")
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--workload", "tiny", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "vertices/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("mesh vertices/sec") and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+
+
+def test_reference_arm_non_zero_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--workload", "tiny", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_gpu_arm_fails_loudly_without_a_device():
+    r = subprocess.run([sys.executable, BENCH, "--workload", "tiny", "--steps", "1"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_traffic_file_is_well_formed():
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        t = json.load(f)
+    for wl, fams in t.items():
+        for fam, ent in fams.items():
+            assert ent["dram_bytes_per_launch"] > 0 and isinstance(ent["note"], str)
