@@ -27,6 +27,18 @@ import sys
 import threading
 import time
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when the
+# box sets NCCL_DEBUG), so the real stdout is set aside for the result line and fd 1 is pointed at stderr for everything
+# else, before anything is imported that could write.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(result: dict) -> None:
+    _RESULT_OUT.write(json.dumps(result) + "\n")
+    _RESULT_OUT.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (os.path.join(ROOT, "surface-texture-inpainting-net_b200"), ROOT):
     if p not in sys.path:
@@ -169,7 +181,7 @@ def run_reference(args, wl, rank, world):
     v = n0 / dt
     what = "forward (eval, no_grad)" if infer else "fwd+loss+bwd"
     sample = f"1 of {wl['batch']} graphs ({n0} vertices), {what}, {steps} timed steps after {warm} warm-up"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": v, "unit": "vertices/s", "n_gpus": 0,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -177,7 +189,7 @@ def run_reference(args, wl, rank, world):
         "cpu_baseline": {"value": v, "unit": "vertices/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def cpu_baseline(wl, budget_s=25.0):
@@ -470,7 +482,7 @@ def main():
         cpu = cpu_baseline(wl)
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": value,
             "unit": "vertices/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -485,7 +497,7 @@ def main():
                              "no explicit flush"},
             "e2e": e2e, "e2e_cached_structure": cached, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 

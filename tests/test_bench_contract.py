@@ -27,6 +27,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
 
 
+def test_result_line_is_alone_on_stdout_even_if_a_library_writes_to_fd_1():
+    """NCCL prints its version banner to fd 1 on the GPU boxes; bench.py keeps the real stdout for the result line."""
+    code = ("import os, runpy, sys; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'tiny', '--steps', '1', "
+            "'--warmup', '1']; import bench; os.write(1, b'NCCL version 0.0.0\\n'); bench.main()")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference"
+    assert "NCCL version 0.0.0" in r.stderr
+
+
 def test_reference_arm_non_zero_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--workload", "tiny", "--gpus", "2"],
