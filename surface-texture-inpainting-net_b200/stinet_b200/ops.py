@@ -130,7 +130,8 @@ class EdgeMessageFn(Function):
         ld = _ld(pq)
         ctx.csr = csr
         ctx.shape = (n, h)
-        ctx.masked = h % 4 == 0 and ld % 4 == 0 and pq.data_ptr() % 16 == 0
+        # decisions are only worth storing when a backward pass will read them (not under no_grad / inference)
+        ctx.masked = ctx.needs_input_grad[0] and h % 4 == 0 and ld % 4 == 0 and pq.data_ptr() % 16 == 0
         if ctx.masked:
             mask = torch.empty((max(csr.e, 1), h // 4), dtype=torch.uint8, device=pq.device)
             _abi.call("stinet_edge_message_fwd_mask", pq.data_ptr(), ld, pq.data_ptr() + 4 * h, ld,
