@@ -24,10 +24,21 @@ from typing import List, Tuple
 
 import torch
 
+from ._abi import StinetError
+
 
 def vertex_clustering(coords: torch.Tensor, edge_index: torch.Tensor, voxel_size: float
                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """-> (new_coords float32 [Nc,3], trace int64 [N], coarse edge_index int64 [2,Ec] sorted by (vertex, neighbour))"""
+    """-> (new_coords float32 [Nc,3], trace int64 [N], coarse edge_index int64 [2,Ec] sorted by (vertex, neighbour)).
+    Like every other entry of the package this runs on the device only; the tensor program underneath is
+    device-agnostic, which is what tests/test_hierarchy.py uses to pin it on host tensors."""
+    if not (coords.is_cuda and edge_index.is_cuda):
+        raise StinetError("stinet_b200.hierarchy works on CUDA tensors (there is no CPU path in this package)")
+    return _vertex_clustering_program(coords, edge_index, voxel_size)
+
+
+def _vertex_clustering_program(coords: torch.Tensor, edge_index: torch.Tensor, voxel_size: float
+                               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     assert coords.dim() == 2 and coords.size(1) == 3 and coords.dtype in (torch.float32, torch.float64)
     assert edge_index.dim() == 2 and edge_index.size(0) == 2 and edge_index.dtype == torch.int64
     n = coords.size(0)
@@ -55,12 +66,13 @@ def vertex_clustering(coords: torch.Tensor, edge_index: torch.Tensor, voxel_size
     return (sums / cnt).to(torch.float32), trace, coarse
 
 
-def build_hierarchy(coords: torch.Tensor, edge_index: torch.Tensor, voxel_sizes: List[float]):
+def build_hierarchy(coords: torch.Tensor, edge_index: torch.Tensor, voxel_sizes: List[float], _step=None):
     """Chains the levels as reference process_frame does (:404-420): level l+1 is clustered from level l's float32
     coordinates and coarse edges.  -> list of dicts {coords, edge_index, trace (absent at level 0)}; `trace` maps
     level l-1 vertices to level l (the `hierarchy_trace_index_l` the model consumes)."""
     levels = [{"coords": coords, "edge_index": edge_index}]
+    step = _step or vertex_clustering
     for voxel in voxel_sizes:
-        c, t, e = vertex_clustering(levels[-1]["coords"], levels[-1]["edge_index"], float(voxel))
+        c, t, e = step(levels[-1]["coords"], levels[-1]["edge_index"], float(voxel))
         levels.append({"coords": c, "edge_index": e, "trace": t})
     return levels

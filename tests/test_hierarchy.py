@@ -33,11 +33,13 @@ def test_oracle_matches_reference_golden(path):
 
 
 def _check_product(path, device):
-    from stinet_b200.hierarchy import build_hierarchy
+    from stinet_b200 import hierarchy
     fix = torch.load(path, weights_only=False)
     ref = fix["levels"]
-    got = build_hierarchy(ref[0]["coords"].to(device), ref[0]["edges"].t().contiguous().to(device),
-                          [l["voxel"] for l in ref[1:]])
+    # the public entry points are device-only; on host tensors the test drives the tensor program underneath directly
+    step = None if device == "cuda" else hierarchy._vertex_clustering_program
+    got = hierarchy.build_hierarchy(ref[0]["coords"].to(device), ref[0]["edges"].t().contiguous().to(device),
+                                    [l["voxel"] for l in ref[1:]], _step=step)
     assert len(got) == len(ref)
     for g, r in zip(got[1:], ref[1:]):
         assert torch.equal(g["trace"].cpu(), r["trace"])
@@ -61,6 +63,12 @@ def test_product_function_matches_reference_golden_on_host_tensors(path):
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-3] for p in FIXTURES])
 def test_product_function_matches_reference_golden_on_device(path):
     _check_product(path, "cuda")
+
+
+def test_public_entry_refuses_host_tensors():
+    from stinet_b200 import _abi, hierarchy
+    with pytest.raises(_abi.StinetError):
+        hierarchy.vertex_clustering(torch.zeros(4, 3), torch.zeros((2, 0), dtype=torch.int64), 0.5)
 
 
 def test_floor_division_semantics_match_numpy():
