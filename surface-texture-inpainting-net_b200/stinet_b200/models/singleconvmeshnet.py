@@ -16,7 +16,7 @@ propagation step trains.
 from __future__ import annotations
 
 import torch
-from torch.nn import BatchNorm1d, LeakyReLU, Linear as Lin, ReLU, Sequential as Seq, functional as F
+from torch.nn import BatchNorm1d, Linear as Lin, ReLU, Sequential as Seq, functional as F
 from torch.utils import checkpoint
 
 from .. import ops
@@ -29,47 +29,34 @@ class SingleConvMeshNet(torch.nn.Module):
     def __init__(self, feature_number, num_propagation_steps, filter_sizes, num_classes=3, pooling_method='mean',
                  aggr='mean', precision='fp32'):
         super().__init__()
-        activation = 'ReLU'
-        curr_size = feature_number
-        inplace = False
         self._pooling_method = pooling_method
-        if activation == 'ReLU':
-            self._activation, self._act = ReLU, F.relu
-        else:
-            self._activation, self._act = LeakyReLU, F.leaky_relu
-        left, right = [], []
+        self._activation, self._act = ReLU, F.relu                  # the reference hard-wires 'ReLU' (:17, :24-26)
         self._graph_levels = len(filter_sizes)
-        for level in range(len(filter_sizes)):
-            if level < len(filter_sizes) - 1:
-                if level == 0:                                                   # translation invariant first conv (:44-47)
-                    left_geo = [get_gcn_filter(curr_size, filter_sizes[level], self._activation, aggregation=aggr,
-                                               module=EdgeConvTransInv, double_input=False, with_norm=True)]
-                else:
-                    left_geo = [get_gcn_filter(curr_size, filter_sizes[level], self._activation, aggregation=aggr,
-                                               with_norm=True)]
-                for _ in range(num_propagation_steps - 1):
-                    left_geo.append(get_gcn_filter(filter_sizes[level], filter_sizes[level], self._activation,
-                                                   aggregation=aggr, with_norm=True))
-                curr_size = filter_sizes[level] + filter_sizes[level + 1]        # decoder input: skip || unpooled (:58)
-                right_geo = [get_gcn_filter(curr_size, filter_sizes[level], self._activation, aggregation=aggr,
-                                            with_norm=True)]
-                for _ in range(num_propagation_steps - 1):
-                    right_geo.append(get_gcn_filter(filter_sizes[level], filter_sizes[level], self._activation,
-                                                    aggregation=aggr, with_norm=True))
-                right.append(self.ResBlock(right_geo, self._act))
-                curr_size = filter_sizes[level]
-            else:
-                left_geo = [get_gcn_filter(curr_size, filter_sizes[level], self._activation, aggregation=aggr,
-                                           with_norm=True)]
-                for _ in range(num_propagation_steps - 1):
-                    left_geo.append(get_gcn_filter(filter_sizes[level], filter_sizes[level], self._activation,
-                                                   aggregation=aggr, with_norm=True))
-            left.append(self.ResBlock(left_geo, self._act))
-        final = [Seq(Lin(filter_sizes[0], filter_sizes[0] // 2), BatchNorm1d(filter_sizes[0] // 2),
-                     self._activation(inplace=inplace), Lin(filter_sizes[0] // 2, num_classes))]
-        self.left_geo_cnns = torch.nn.ModuleList(left)
-        self.right_geo_cnns = torch.nn.ModuleList(right)
-        self.final_convs = torch.nn.ModuleList(final)
+        widths = list(filter_sizes)
+
+        def conv(din, dout, first=False):
+            # every conv carries BatchNorm over edges; only the very first one is translation invariant (:44-51)
+            extra = dict(module=EdgeConvTransInv, double_input=False) if first else {}
+            return get_gcn_filter(din, dout, self._activation, aggregation=aggr, with_norm=True, **extra)
+
+        def stack(din, dout, first=False):
+            return [conv(din, dout, first)] + [conv(dout, dout) for _ in range(num_propagation_steps - 1)]
+
+        # Modules are created level by level, encoder stack before decoder stack, exactly as the reference does: a seeded
+        # construction then draws the same initial weights (tests/test_singleconv.py checks it bit for bit).
+        encoders, decoders = [], []
+        din = feature_number
+        for level, width in enumerate(widths):
+            enc = stack(din, width, first=(level == 0))
+            if level + 1 < len(widths):
+                decoders.append(self.ResBlock(stack(width + widths[level + 1], width), self._act))   # skip || unpooled (:58)
+            encoders.append(self.ResBlock(enc, self._act))
+            din = width
+        head = Seq(Lin(widths[0], widths[0] // 2), BatchNorm1d(widths[0] // 2), self._activation(inplace=False),
+                   Lin(widths[0] // 2, num_classes))
+        self.left_geo_cnns = torch.nn.ModuleList(encoders)
+        self.right_geo_cnns = torch.nn.ModuleList(decoders)
+        self.final_convs = torch.nn.ModuleList([head])
         self.set_precision(precision)
 
     def set_precision(self, precision: str):

@@ -97,6 +97,19 @@ def test_host_logic_with_stand_in_kernels_matches_reference_golden(name, torch_s
     check_against_golden(net.train(), fix["batch"], fix)
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+def test_seeded_construction_draws_the_reference_weights(name):
+    """Same module creation order as the reference => torch.manual_seed(49) + construction reproduces the golden
+    state_dict (minted from the reference's own constructor under the same seed) bit for bit."""
+    from stinet_b200.models.singleconvmeshnet import SingleConvMeshNet
+    fix = load(name)
+    torch.manual_seed(49)
+    sd = SingleConvMeshNet(**fix["kwargs"]).state_dict()
+    assert list(sd) == list(fix["state_dict"])
+    for k, v in sd.items():
+        assert torch.equal(v, fix["state_dict"][k]), k
+
+
 def test_edges_as_clusters_index_plumbing(torch_stand_ins):
     """x_i / x_j gathers and the mean over in-edges expressed through the pooling structures: members of a target's
     cluster are its in-edges in original order, trace32 is the end point of every original edge."""
