@@ -31,6 +31,11 @@ CASES = {
              pooling_method="mean", aggr="mean"),
         [("icosphere", dict(subdiv=2, n_levels=2, seed=61, mask_radius=2)),
          ("icosphere", dict(subdiv=2, n_levels=2, seed=62, mask_radius=2))]),
+    # two propagation steps: the reference's in-place residual (:107) makes its own backward raise, so forward only
+    "singleconv_ico_steps2_fwd": (
+        dict(feature_number=10, num_propagation_steps=2, filter_sizes=[8, 12], num_classes=4,
+             pooling_method="mean", aggr="mean"),
+        [("icosphere", dict(subdiv=2, n_levels=1, seed=64, mask_radius=2))]),
     "singleconv_ico_max_b1": (
         dict(feature_number=10, num_propagation_steps=1, filter_sizes=[12, 20], num_classes=3,
              pooling_method="max", aggr="mean"),
@@ -60,14 +65,17 @@ def main():
         batch.x.requires_grad_(True)
         out = net(batch)
         loss = out.square().mean()
-        loss.backward()
+        forward_only = kwargs["num_propagation_steps"] > 1
+        if not forward_only:
+            loss.backward()
         fix = {
             "kwargs": kwargs, "specs": specs, "state_dict": state,
             "sample": {k: (batch[k].detach().clone() if torch.is_tensor(batch[k]) else batch[k])
                        for k in batch.keys if k not in ("ptr", "num_graphs")},
             "out": out.detach().clone(), "loss": loss.detach().clone(),
-            "grads": {k: p.grad.detach().clone() for k, p in net.named_parameters()},
-            "grad_x": batch.x.grad.detach().clone(),
+            "forward_only": forward_only,
+            "grads": None if forward_only else {k: p.grad.detach().clone() for k, p in net.named_parameters()},
+            "grad_x": None if forward_only else batch.x.grad.detach().clone(),
             "buffers_after": {k: v.detach().clone() for k, v in net.named_buffers()},
         }
         path = os.path.join(HERE, "singleconv", f"{name}.pt")
