@@ -30,6 +30,18 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.stinet_abi_version() == 1
 
 
+def test_ctypes_arity_matches_the_header_prototypes():
+    """Every prototype in include/stinet_b200.h has as many parameters as its ctypes signature lists argument types
+    (a silent mismatch would only surface as stack garbage on the GPU box)."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|size_t|long long|const char\*)\s+(stinet_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) == len(_abi.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_abi.SIGNATURES[name][1]), f"{name}: header has {n} parameters, binding {len(_abi.SIGNATURES[name][1])}"
+
+
 def test_workspace_queries_are_pure_host_calls():
     assert _abi.query("stinet_csr_workspace_bytes", 1000, 6000) > 0
     assert _abi.query("stinet_gemm_workspace_bytes", 4096, 256, 64, 0) > 0
