@@ -28,15 +28,23 @@ import threading
 import time
 
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when the
-# box sets NCCL_DEBUG), so the real stdout is set aside for the result line and fd 1 is pointed at stderr for everything
-# else, before anything is imported that could write.
-_RESULT_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+# box sets NCCL_DEBUG), so main() sets the real stdout aside for the result line and points fd 1 at stderr for
+# everything else.
+_RESULT_OUT = None
+
+
+def reserve_stdout() -> None:
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(result: dict) -> None:
-    _RESULT_OUT.write(json.dumps(result) + "\n")
-    _RESULT_OUT.flush()
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(result) + "\n")
+    out.flush()
 
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -246,6 +254,7 @@ def main():
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket timed region 1 with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
+    reserve_stdout()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -29,8 +29,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 
 def test_result_line_is_alone_on_stdout_even_if_a_library_writes_to_fd_1():
     """NCCL prints its version banner to fd 1 on the GPU boxes; bench.py keeps the real stdout for the result line."""
-    code = ("import os, runpy, sys; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'tiny', '--steps', '1', "
-            "'--warmup', '1']; import bench; os.write(1, b'NCCL version 0.0.0\\n'); bench.main()")
+    code = ("import os, sys; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'tiny', '--steps', '1', "
+            "'--warmup', '1']; import bench; real = bench.run_reference; "
+            "bench.run_reference = lambda *a: (os.write(1, b'NCCL version 0.0.0\\n'), real(*a)); bench.main()")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-500:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
