@@ -92,6 +92,26 @@ def peaks():
     return dict(FALLBACK_PEAKS), "fallback"
 
 
+def path_roofline(summ: dict, steps: int, hbm_gbs: float, bf16_tflops: float, passes: int, rate: float) -> dict:
+    """the path's roofline time = sum over kernels of max(algorithmic bytes / HBM peak, flops / tensor peak).
+    `summ` = KernelProfiler.summary() of `steps` eager steps.  Two tensor ceilings are reported: the dense bf16 peak,
+    and the ceiling of the arithmetic mode in use (peak * rate / passes, e.g. 3 TF32 passes at half rate for fp32)."""
+    t_bf16 = t_mode = t_meas = 0.0
+    for key, r in summ.items():
+        t_b = r["bytes"] / (hbm_gbs * 1e9)
+        dense = key.startswith("linear")
+        t_f = r["flops"] / (bf16_tflops * 1e12) if dense else 0.0
+        t_bf16 += max(t_b, t_f)
+        t_mode += max(t_b, t_f * passes / rate)
+        t_meas += r["ms"] * 1e-3
+    per = 1e3 / max(steps, 1)
+    return {"roofline_ms_per_step": t_bf16 * per, "roofline_ms_per_step_mode_ceiling": t_mode * per,
+            "measured_ms_per_step_eager": t_meas * per,
+            "note": "sum over kernels of max(algorithmic bytes / HBM peak, flops / tensor peak); HBM bytes follow the "
+                    "no-cache-reuse convention of SURVEY 8d, so this is an upper bound on the time a perfect "
+                    "implementation needs"}
+
+
 def masked_l1(out, b):
     """trainer glue that stays PyTorch: reference trainers/inpainting3d_trainer.py:127-137"""
     composed = torch.where((b.mask > 0).expand_as(b.color), out, b.color)
@@ -466,6 +486,14 @@ def main():
             ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth"}
+        try:                                               # never let a reporting extra take the bench down
+            passes_, rate_ = {"fp32": (3, 0.5), "bf16x3": (3, 1.0), "bf16": (1, 1.0), "tf32": (1, 0.5)}[precision]
+            roofline["path"] = path_roofline(summ, 2, pk["hbm_gbs"], bf16_peak, passes_, rate_)
+            roofline["path"]["frac_of_timed_step"] = roofline["path"]["roofline_ms_per_step"] / (ms / K)
+            roofline["path"]["frac_of_timed_step_mode_ceiling"] = \
+                roofline["path"]["roofline_ms_per_step_mode_ceiling"] / (ms / K)
+        except Exception as e:  # noqa: BLE001
+            roofline["path"] = {"error": repr(e)}
         roofline["share_of_step"] = r["ms"] / total
         roofline["ms_per_launch"] = r["ms"] / r["calls"]
         # measured DRAM traffic per launch of the dominant kernels (ncu --set full, profiles/): largest shape of each

@@ -59,3 +59,15 @@ def test_traffic_file_is_well_formed():
     for wl, fams in t.items():
         for fam, ent in fams.items():
             assert ent["dram_bytes_per_launch"] > 0 and isinstance(ent["note"], str)
+
+
+def test_path_roofline_sums_the_per_kernel_bounds():
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    summ = {"linear_fwd[8x8]": {"calls": 2, "ms": 4.0, "bytes": 1e9, "flops": 2e12},       # tensor bound: 2e12 / 1e15 = 2 ms
+            "edge_message_fwd[H8]": {"calls": 2, "ms": 1.0, "bytes": 5e9, "flops": 1e9}}    # HBM bound: 5e9 / 5e12 = 1 ms
+    r = bench.path_roofline(summ, 2, hbm_gbs=5000.0, bf16_tflops=1000.0, passes=3, rate=0.5)
+    assert abs(r["roofline_ms_per_step"] - (2.0 + 1.0) / 2) < 1e-9
+    assert abs(r["roofline_ms_per_step_mode_ceiling"] - (12.0 + 1.0) / 2) < 1e-9
+    assert abs(r["measured_ms_per_step_eager"] - 2.5) < 1e-9
