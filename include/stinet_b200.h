@@ -214,6 +214,40 @@ int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t ld
                         int64_t ldw, float* dbias, int64_t M, int64_t N, int64_t K, int precision, void* workspace,
                         size_t workspace_bytes, stinet_stream_t stream);
 
+/* ---- dense layers on operand PLANES (the fp32-parity path of the dense layers; same reference call sites as above).
+ * A matrix x is handed to the tensor cores as two fp16 planes of the scaled matrix x 2^s:
+ *     hi = fp16(x 2^s),  lo = fp16((x 2^s - hi) 2^11),  exp = -s            (hi + lo 2^-11 = x 2^s to 22 significand bits)
+ * with s picked from amax = max|x| so that amax 2^s lies in [2^14, 2^15): fp16's range is used in full, every element
+ * down to amax 2^-28 keeps its 22 bits and smaller ones an absolute error below amax 2^-50.  `amax` may be any upper
+ * bound of max|x| within a factor ~2^16 (producers that know a bound skip the reduction).  The GEMMs evaluate
+ * hi*hi + (hi*lo + lo*hi) 2^-11 on tcgen05 kind::f16 with fp32 accumulation (two TMEM accumulators, promotion to
+ * round-to-nearest registers every 128 reduction elements) and undo the scales in the epilogue: fp32-class results
+ * (the 1e-5 parity bar) at the full 16-bit tensor rate.  passes = 3: as described; passes = 1: hi planes only
+ * (11 significand bits, the reduced-precision mode; lo pointers may be NULL).
+ * Planes are row-major with pitch `ldp` (elements, a multiple of 8), laid out like the matrix they were split from.
+ *   f16_amax   amax[0] = max|x| (as an fp32 bit pattern; NaN propagates).  Resets amax first.
+ *   f16_split  reads amax[0], writes hi, lo and exp_out[0] = -s.
+ *   colsum     dbias[N] = sum_m dC[m,:] * (rowmask ? rowmask[m] > 0 : 1), deterministic two-stage column sums
+ *              (workspace: stinet_gemm_workspace_bytes(M, N, 1, STINET_PREC_FP32)). */
+int stinet_f16_amax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* amax, stinet_stream_t stream);
+int stinet_f16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* amax, void* hi, void* lo,
+                     int64_t ldp, int32_t* exp_out, stinet_stream_t stream);
+/* workspace for the three calls below: stinet_gemm_workspace_bytes(M, N, K, STINET_PREC_FP32) */
+int stinet_linear_fwd_f16(const void* A_hi, const void* A_lo, int64_t lda, const int32_t* a_exp, const void* W_hi,
+                          const void* W_lo, int64_t ldw, const int32_t* w_exp, const float* bias,
+                          const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int passes,
+                          void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+int stinet_linear_dgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* W_hi,
+                            const void* W_lo, int64_t ldw, const int32_t* w_exp, float* dA, int64_t lda, int64_t M,
+                            int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
+                            stinet_stream_t stream);
+int stinet_linear_wgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* A_hi,
+                            const void* A_lo, int64_t lda, const int32_t* a_exp, float* dW, int64_t ldw, int64_t M,
+                            int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
+                            stinet_stream_t stream);
+int stinet_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int64_t M, int64_t N, float* dbias,
+                  void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+
 /* ---- per-step graph metrics (replace utils/metrics/graph_metrics.py:6-72 as called from
  * trainers/inpainting3d_trainer.py:254-263) on the level-0 CSR by target.  Scalar results are written to `out` on the
  * device (float[1], psnr float[2] = {score, rows used}); reductions are deterministic (double partials, fixed order).

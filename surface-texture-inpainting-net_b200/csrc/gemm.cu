@@ -6,6 +6,7 @@
 // Fallback for operands TMA cannot address (row pitch not a multiple of 16 B: the 10-channel input, the 3-channel
 // head): 128x64x16 FFMA tiles, 256 threads, 8x4 outputs per thread, register-staged double buffering.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -303,6 +304,110 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
   }
 }
 
+
+// masked column sums of dC [M,N] (dbias): two deterministic stages, partials in `part`
+static void run_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int64_t M, int64_t N, float* dbias,
+                       float* part, cudaStream_t s) {
+  const int rpc = colsum_rows(M > 0 ? M : 1, N);
+  const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
+  const bool vec = !(N & 3) && !(ldc & 3) && aligned16(dC);
+  if (vec && N > 64) {
+    dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
+    K(colsum_partial_vec_kernel<32><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, part));
+  } else if (vec) {
+    dim3 g2((unsigned)ceil_div(N, 64), (unsigned)chunks);
+    K(colsum_partial_vec_kernel<16><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, part));
+  } else {
+    dim3 g2((unsigned)ceil_div(N, 32), (unsigned)chunks);
+    K(colsum_partial_kernel<<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, part));
+  }
+  K(colsum_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(part, chunks, (int)N, dbias));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// operand planes for the fp16 tensor-core modes (see include/stinet_b200.h, "dense layers on operand PLANES")
+
+// max |x| as a bit pattern: non-negative floats order like their bit patterns (NaN above inf, so NaN propagates).
+// One atomicMax per CTA, skipped when the CTA cannot raise the value (a stale read can only under-estimate it).
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
+                                                   unsigned* __restrict__ amax) {
+  __shared__ unsigned sm[8];
+  unsigned m = 0;
+  if ((cols & 3) == 0 && (ldx & 3) == 0 && aligned16(x)) {
+    const int cpr = cols >> 2;
+    const int64_t total = rows * cpr;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / cpr;
+      const int c = (int)(idx - r * cpr) << 2;
+      const float4 v = ld_stream(reinterpret_cast<const float4*>(x + r * ldx + c));
+      m = max(max(m, __float_as_uint(v.x) & 0x7FFFFFFFu), __float_as_uint(v.y) & 0x7FFFFFFFu);
+      m = max(max(m, __float_as_uint(v.z) & 0x7FFFFFFFu), __float_as_uint(v.w) & 0x7FFFFFFFu);
+    }
+  } else {
+    const int64_t total = rows * cols;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / cols;
+      m = max(m, __float_as_uint(x[r * ldx + (idx - r * cols)]) & 0x7FFFFFFFu);
+    }
+  }
+  m = __reduce_max_sync(0xFFFFFFFFu, m);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = max(m, sm[w]);
+    if (m > *reinterpret_cast<volatile unsigned*>(amax)) atomicMax(amax, m);
+  }
+}
+
+// s with amax 2^s in [2^14, 2^15) (amax = 0, inf or NaN: s = 0), clamped so that 2^s and 2^-s stay normal floats
+__device__ __forceinline__ int plane_shift(unsigned amax_bits) {
+  const int e = (int)((amax_bits >> 23) & 0xFFu);
+  if ((amax_bits & 0x7FFFFFFFu) == 0u || e == 255) return 0;
+  const int s = 15 - (max(e, 1) - 126);
+  return max(-110, min(110, s));
+}
+__device__ __forceinline__ void split_one(float x, float scale, __half& hi, __half& lo) {
+  const float xs = x * scale;
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn((xs - __half2float(hi)) * 2048.f);
+}
+
+// x [rows, cols] fp32 -> hi / lo fp16 planes (pitch ldp) of x 2^s; exp_out = -s.  Vector form: 8 elements per thread.
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
+                                                        const unsigned* __restrict__ amax, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, int64_t ldp, int32_t* __restrict__ exp_out) {
+  const int sft = plane_shift(__ldg(amax));
+  const float scale = __uint_as_float((uint32_t)(127 + sft) << 23);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = -sft;
+  if ((cols & 7) == 0 && (ldx & 3) == 0 && aligned16(x)) {
+    const int cpr = cols >> 3;
+    const int64_t total = rows * cpr;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / cpr;
+      const int c = (int)(idx - r * cpr) << 3;
+      const float4 a = ld_stream(reinterpret_cast<const float4*>(x + r * ldx + c));
+      const float4 b = ld_stream(reinterpret_cast<const float4*>(x + r * ldx + c + 4));
+      __half h[8], l[8];
+      split_one(a.x, scale, h[0], l[0]); split_one(a.y, scale, h[1], l[1]);
+      split_one(a.z, scale, h[2], l[2]); split_one(a.w, scale, h[3], l[3]);
+      split_one(b.x, scale, h[4], l[4]); split_one(b.y, scale, h[5], l[5]);
+      split_one(b.z, scale, h[6], l[6]); split_one(b.w, scale, h[7], l[7]);
+      *reinterpret_cast<uint4*>(hi + r * ldp + c) = *reinterpret_cast<const uint4*>(h);
+      if (lo != nullptr) *reinterpret_cast<uint4*>(lo + r * ldp + c) = *reinterpret_cast<const uint4*>(l);
+    }
+  } else {
+    const int64_t total = rows * cols;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / cols;
+      const int64_t c = idx - r * cols;
+      __half h, l;
+      split_one(x[r * ldx + c], scale, h, l);
+      hi[r * ldp + c] = h;
+      if (lo != nullptr) lo[r * ldp + c] = l;
+    }
+  }
+}
 
 // fp32 -> bf16 cast of a row-major matrix (bf16 mode: the tensor-core kernel reads bf16 operands through TMA).
 // cols % 8 == 0, 16 B aligned rows on both sides; one thread converts 8 elements.
@@ -649,21 +754,119 @@ extern "C" int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A,
                                                                       nullptr));
     }
   }
-  if (dbias) {
-    const int rpc = colsum_rows(M > 0 ? M : 1, N);
-    const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
-    const bool vec = !(N & 3) && !(ldc & 3) && aligned16(dC);
-    if (vec && N > 64) {
-      dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
-      K(colsum_partial_vec_kernel<32><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, w.colsum));
-    } else if (vec) {
-      dim3 g2((unsigned)ceil_div(N, 64), (unsigned)chunks);
-      K(colsum_partial_vec_kernel<16><<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, w.colsum));
-    } else {
-      dim3 g2((unsigned)ceil_div(N, 32), (unsigned)chunks);
-      K(colsum_partial_kernel<<<g2, 256, 0, s>>>(dC, ldc, rowmask, M, (int)N, rpc, w.colsum));
-    }
-    K(colsum_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(w.colsum, chunks, (int)N, dbias));
-  }
+  if (dbias) run_colsum(dC, ldc, rowmask, M, N, dbias, w.colsum, s);
   return check_launch("linear_wgrad");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dense layers on fp16 operand planes
+
+extern "C" int stinet_f16_amax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* amax, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && amax, STINET_ERR_ARG, "f16_amax: null pointer");
+  STINET_REQUIRE(rows >= 0 && cols > 0 && ldx >= cols && cols < (1ll << 31), STINET_ERR_ARG, "f16_amax: bad shape");
+  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float), s);
+  STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "f16_amax: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (rows == 0) return STINET_OK;
+  K(amax_kernel<<<wave_grid(rows * ceil_div(cols, 4), 256 * 4, 8), 256, 0, s>>>(x, ldx, rows, (int)cols,
+                                                                               reinterpret_cast<unsigned*>(amax)));
+  return check_launch("f16_amax");
+}
+
+extern "C" int stinet_f16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* amax, void* hi, void* lo,
+                                int64_t ldp, int32_t* exp_out, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && amax && hi && exp_out, STINET_ERR_ARG, "f16_split: null pointer");
+  STINET_REQUIRE(rows >= 0 && cols > 0 && ldx >= cols && ldp >= cols && ldp % 8 == 0 && cols < (1ll << 31), STINET_ERR_ARG,
+                 "f16_split: bad shape (plane pitch must be a multiple of 8 elements)");
+  STINET_REQUIRE(aligned16(hi) && (lo == nullptr || aligned16(lo)), STINET_ERR_ARG, "f16_split: planes must be 16-byte aligned");
+  // rows == 0 still has to publish the exponent: one CTA does
+  K(split_f16_kernel<<<wave_grid(rows * ceil_div(cols, 8), 256 * 2, 8), 256, 0, s>>>(
+      x, ldx, rows, (int)cols, reinterpret_cast<const unsigned*>(amax), static_cast<__half*>(hi), static_cast<__half*>(lo),
+      ldp, exp_out));
+  return check_launch("f16_split");
+}
+
+extern "C" int stinet_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int64_t M, int64_t N, float* dbias,
+                             void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(dC && dbias, STINET_ERR_ARG, "colsum: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && ldc >= N, STINET_ERR_ARG, "colsum: bad shape");
+  GemmWs w = carve_gemm(workspace, M, N, 1, STINET_PREC_FP32);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "colsum: workspace %zu < %zu", workspace_bytes,
+                 w.bytes);
+  run_colsum(dC, ldc, rowmask, M, N, dbias, w.colsum, s);
+  return check_launch("colsum");
+}
+
+static int f16_mode(int passes) { return passes == 3 ? tc::MODE_F16X3 : passes == 1 ? tc::MODE_F16X1 : -1; }
+
+// one planes GEMM  C[I,J] = sum_t A'(i,t) B'(t,j) 2^(a_exp + b_exp), split over t when the tiles do not fill the SMs
+static int run_planes(tc::Problem p, int max_splits, const float* bias, const int32_t* rowmask, float* C, int64_t ldc,
+                      const GemmWs& w, bool have_ws, const char* what, cudaStream_t s) {
+  STINET_REQUIRE(tc::eligible(p), STINET_ERR_UNSUPPORTED,
+                 "%s: operand planes / output not addressable by TMA (16-byte pitches, output width %% 4)", what);
+  const TcSplit sp = tc_split(p.I, p.J, p.T, max_splits);
+  if (sp.splits > 1 && have_ws) {
+    p.C = w.splitk; p.ldc = p.J; p.bias = nullptr; p.rowmask = nullptr;
+    p.splits = sp.splits; p.t_per_split = sp.t_per;
+    int rc = tc::run(p, s);
+    if (rc) return rc;
+    const int64_t IJ = p.I * p.J;
+    if (sp.splits >= 16 && bias == nullptr && !(p.J & 3) && !(ldc & 3) && aligned16(C))
+      K(splitk_reduce_wide_kernel<<<(unsigned)ceil_div(IJ, 128), 256, 0, s>>>(w.splitk, sp.splits, IJ, (int)p.J, C, ldc));
+    else
+      K(splitk_reduce_kernel<<<wave_grid(IJ, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, IJ, (int)p.J, C, ldc, bias, rowmask));
+    return check_launch(what);
+  }
+  p.C = C; p.ldc = ldc; p.bias = bias; p.rowmask = rowmask; p.splits = 1; p.t_per_split = p.T;
+  return tc::run(p, s);
+}
+
+extern "C" int stinet_linear_fwd_f16(const void* A_hi, const void* A_lo, int64_t lda, const int32_t* a_exp, const void* W_hi,
+                                     const void* W_lo, int64_t ldw, const int32_t* w_exp, const float* bias,
+                                     const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                     int passes, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int mode = f16_mode(passes);
+  STINET_REQUIRE(mode >= 0, STINET_ERR_ARG, "linear_fwd_f16: passes must be 1 or 3");
+  STINET_REQUIRE(A_hi && W_hi && C && a_exp && w_exp && (passes == 1 || (A_lo && W_lo)), STINET_ERR_ARG, "linear_fwd_f16: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_fwd_f16: bad shape");
+  if (M == 0) return STINET_OK;
+  GemmWs w = carve_gemm(workspace, M, N, K, STINET_PREC_FP32);
+  tc::Problem p{A_hi, lda, false, W_hi, ldw, false, C, ldc, bias, rowmask, M, N, K, 1, K, mode, A_lo, W_lo, a_exp, w_exp};
+  return run_planes(p, kFwdMaxSplits, bias, rowmask, C, ldc, w, workspace && workspace_bytes >= w.bytes, "linear_fwd_f16", s);
+}
+
+extern "C" int stinet_linear_dgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* W_hi,
+                                       const void* W_lo, int64_t ldw, const int32_t* w_exp, float* dA, int64_t lda, int64_t M,
+                                       int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
+                                       stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int mode = f16_mode(passes);
+  STINET_REQUIRE(mode >= 0, STINET_ERR_ARG, "linear_dgrad_f16: passes must be 1 or 3");
+  STINET_REQUIRE(dC_hi && W_hi && dA && c_exp && w_exp && (passes == 1 || (dC_lo && W_lo)), STINET_ERR_ARG, "linear_dgrad_f16: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_dgrad_f16: bad shape");
+  if (M == 0) return STINET_OK;
+  GemmWs w = carve_gemm(workspace, M, N, K, STINET_PREC_FP32);
+  // dA[i=m, j=k] = sum_{t=n} dC[m,n] * W[n,k]
+  tc::Problem p{dC_hi, ldc, false, W_hi, ldw, true, dA, lda, nullptr, nullptr, M, K, N, 1, N, mode, dC_lo, W_lo, c_exp, w_exp};
+  return run_planes(p, kFwdMaxSplits, nullptr, nullptr, dA, lda, w, workspace && workspace_bytes >= w.bytes, "linear_dgrad_f16", s);
+}
+
+extern "C" int stinet_linear_wgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* A_hi,
+                                       const void* A_lo, int64_t lda, const int32_t* a_exp, float* dW, int64_t ldw, int64_t M,
+                                       int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
+                                       stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int mode = f16_mode(passes);
+  STINET_REQUIRE(mode >= 0, STINET_ERR_ARG, "linear_wgrad_f16: passes must be 1 or 3");
+  STINET_REQUIRE(dC_hi && A_hi && dW && c_exp && a_exp && (passes == 1 || (dC_lo && A_lo)), STINET_ERR_ARG, "linear_wgrad_f16: null pointer");
+  STINET_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K && ldc >= N, STINET_ERR_ARG, "linear_wgrad_f16: bad shape");
+  GemmWs w = carve_gemm(workspace, M, N, K, STINET_PREC_FP32);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "linear_wgrad_f16: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  // dW[i=n, j=k] = sum_{t=m} dC[m,n] * A[m,k]
+  tc::Problem p{dC_hi, ldc, true, A_hi, lda, true, dW, ldw, nullptr, nullptr, N, K, M, 1, M, mode, dC_lo, A_lo, c_exp, a_exp};
+  return run_planes(p, kWgradMaxSplits, nullptr, nullptr, dW, ldw, w, true, "linear_wgrad_f16", s);
 }

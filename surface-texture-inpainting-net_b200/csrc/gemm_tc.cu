@@ -54,6 +54,8 @@ struct TcArgs {
   int tiles_j, tiles_ij, n_units;  // work units = (split z, row tile, column tile), column tile fastest
   int promote;                     // k-blocks accumulated in TMEM before the partial sum is promoted to registers
   int split_acc;                   // fp32 mode: keep the hi*lo + lo*hi correction terms in their own TMEM accumulator
+  const int32_t* a_exp;            // F16 modes: the result is multiplied by 2^(*a_exp + *b_exp) (operand plane scales)
+  const int32_t* b_exp;
 };
 
 #ifdef STINET_TC_DEBUG
@@ -150,9 +152,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-template <bool BF16>
+template <bool K16>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (BF16) {
+  if (K16) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
@@ -205,10 +207,11 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 
 template <int BN, int MODE>
 struct Cfg {
-  static constexpr bool kBf16 = MODE == MODE_BF16 || MODE == MODE_BF16X3;
+  static constexpr bool kF16 = MODE == MODE_F16X3 || MODE == MODE_F16X1;      // scaled fp16 planes, result descaled
+  static constexpr bool kBf16 = MODE == MODE_BF16 || MODE == MODE_BF16X3 || kF16;  // 16-bit operands on kind::f16
   static constexpr bool kConv = MODE == MODE_TF32X3;               // operand split done in smem by the split warps
-  static constexpr bool kPre = MODE == MODE_BF16X3 || MODE == MODE_TF32X3P;  // operand split done by the caller in HBM
-  static constexpr bool kFp32 = MODE == MODE_TF32X3 || MODE == MODE_TF32X3P;   // fp32-class result: promotion + correction accumulator
+  static constexpr bool kPre = MODE == MODE_BF16X3 || MODE == MODE_TF32X3P || MODE == MODE_F16X3;  // split done by the caller in HBM
+  static constexpr bool kFp32 = MODE == MODE_TF32X3 || MODE == MODE_TF32X3P || MODE == MODE_F16X3; // fp32-class result: promotion + correction accumulator
   static constexpr bool kSplit = kConv || kPre;                    // stage holds hi and lo tiles, three MMAs per k-step
   static constexpr int kElemBytes = kBf16 ? 2 : 4;
   static constexpr int BKE = kRowBytes / kElemBytes;  // reduction elements per stage: 32 fp32 / 64 bf16
@@ -336,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ===== MMA issuer =====
       // instruction descriptor: D fp32, A/B tf32 or bf16, majors, N>>3, M>>4
-      const uint32_t fmt = kBf16 ? 1u : 2u;
+      const uint32_t fmt = C_::kF16 ? 0u : (kBf16 ? 1u : 2u);   // operand format: f16 / bf16 / tf32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // per-operand descriptor geometry
@@ -478,7 +481,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t r2[32];
             tmem_ld32(taddr + 2 * BN + cc, r2);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r2[c]));
+            for (int c = 0; c < 32; ++c)   // F16X3: the lo planes carry a factor 2^11
+              r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r2[c]) * (C_::kF16 ? (1.f / 2048.f) : 1.f));
           }
           if (kb0 == 0) {
 #pragma unroll
@@ -498,6 +502,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row0 = w.i0 + q * 32;                      // first row of this warp's lane quarter
       const int row = row0 + lane;                         // the row this thread holds
       const bool add_bias = g.bias != nullptr && row < g.I && (g.rowmask == nullptr || g.rowmask[row] > 0);
+      if (C_::kF16) {
+        // undo the operand scales: exact powers of two, applied in two factors so that neither leaves the fp32 range
+        const int t = __ldg(g.a_exp) + __ldg(g.b_exp);
+        const int t1 = t / 2;
+        const float f1 = __uint_as_float((uint32_t)(127 + max(-126, min(127, t1))) << 23);
+        const float f2 = __uint_as_float((uint32_t)(127 + max(-126, min(127, t - t1))) << 23);
+#pragma unroll
+        for (int c = 0; c < EC; ++c) acc[c] = acc[c] * f1 * f2;
+      }
       if (row0 < g.I) {
 #pragma unroll
         for (int cc = 0; cc < EC; cc += 32) {
@@ -552,8 +565,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D tensor map over a row-major matrix [outer, inner] with row pitch ld (elements); box = [box_outer, box_inner].
-static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, bool bf16,
-                    uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
+static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int bf16,
+                    uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {   // bf16: 0 fp32, 1 bf16, 2 fp16
   EncodeTiledFn fn = encode_fn();
   STINET_REQUIRE(fn != nullptr, STINET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t esz = bf16 ? 2 : 4;
@@ -561,7 +574,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t oute
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = fn(m, bf16 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   STINET_REQUIRE(r == CUDA_SUCCESS, STINET_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner %lld outer %lld ld %lld",
@@ -572,7 +585,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t oute
 template <int BN, bool A_MN, bool B_MN, int MODE>
 static int launch(const Problem& p, cudaStream_t s) {
   using C_ = Cfg<BN, MODE>;
-  constexpr bool bf16 = C_::kBf16;
+  constexpr int bf16 = C_::kF16 ? 2 : (C_::kBf16 ? 1 : 0);
   CUtensorMap tmA, tmB;
   int rc;
   if (!A_MN) rc = make_map(&tmA, p.A, p.T, p.I, p.lda, bf16, C_::BKE, BM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -625,9 +638,14 @@ static int launch(const Problem& p, cudaStream_t s) {
   // to 3e-5 at K = 4096).  STINET_TC_PROMOTE / STINET_TC_SPLITACC override the two knobs for that experiment.
   static const int env_promote = [] { const char* e = getenv("STINET_TC_PROMOTE"); return e ? atoi(e) : 4; }();
   static const int env_split = [] { const char* e = getenv("STINET_TC_SPLITACC"); return e ? atoi(e) : 1; }();
+  // 16-bit k-blocks hold 64 reduction elements: promote every 2 of them; the F16X3 correction accumulator is not optional
+  // (its terms carry the factor 2^11 of the lo planes)
+  static const int env_promote16 = [] { const char* e = getenv("STINET_TC_PROMOTE16"); return e ? atoi(e) : 2; }();
+  const int promote = !C_::kFp32 ? (1 << 28) : C_::kBf16 ? (env_promote16 > 0 ? env_promote16 : 2) : (env_promote > 0 ? env_promote : 4);
+  if (C_::kF16) STINET_REQUIRE(p.a_exp && p.b_exp, STINET_ERR_ARG, "gemm_tc: the fp16 modes need the operand scale exponents");
   TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split,
            tiles_j, tiles_i * tiles_j, (int)units,
-           C_::kFp32 ? (env_promote > 0 ? env_promote : 4) : (1 << 28), C_::kFp32 ? env_split : 0};
+           promote, C_::kFp32 ? (C_::kF16 ? 1 : env_split) : 0, p.a_exp, p.b_exp};
   const unsigned grid = (unsigned)(units < kSMs ? units : kSMs);   // persistent: one CTA per SM walks the work units
   K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, tmC, g));
   return check_launch("gemm_tc");
@@ -649,11 +667,11 @@ static int launch_major(const Problem& p, cudaStream_t s) {
 }
 
 bool eligible(const Problem& p) {
-  const int esz = (p.mode == MODE_BF16 || p.mode == MODE_BF16X3) ? 2 : 4;
+  const int esz = (p.mode == MODE_BF16 || p.mode == MODE_BF16X3 || p.mode == MODE_F16X3 || p.mode == MODE_F16X1) ? 2 : 4;
   const int64_t align_elems = 16 / esz;
   if (p.I <= 0 || p.J <= 0 || p.T <= 0) return false;
   if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C)) return false;
-  if ((p.mode == MODE_BF16X3 || p.mode == MODE_TF32X3P) &&
+  if ((p.mode == MODE_BF16X3 || p.mode == MODE_TF32X3P || p.mode == MODE_F16X3) &&
       (!p.A_lo || !p.B_lo || !aligned16(p.A_lo) || !aligned16(p.B_lo))) return false;
   if (p.lda % align_elems || p.ldb % align_elems) return false;
   if (p.ldc % 4 || p.J % 4) return false;
@@ -671,6 +689,8 @@ int run(const Problem& p, cudaStream_t s) {
     case MODE_BF16: return launch_major<MODE_BF16>(p, s);
     case MODE_BF16X3: return launch_major<MODE_BF16X3>(p, s);
     case MODE_TF32X3P: return launch_major<MODE_TF32X3P>(p, s);
+    case MODE_F16X3: return launch_major<MODE_F16X3>(p, s);
+    case MODE_F16X1: return launch_major<MODE_F16X1>(p, s);
   }
   set_error("gemm_tc: unknown mode %d", p.mode);
   return STINET_ERR_ARG;

@@ -55,10 +55,18 @@ SIGNATURES = {
     "stinet_linear_fwd": (I, [P, I64, P, I64, P, P, P, I64, I64, I64, I64, I, P, SZ, P]),
     "stinet_linear_dgrad": (I, [P, I64, P, I64, P, I64, I64, I64, I64, I, P, SZ, P]),
     "stinet_linear_wgrad": (I, [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I, P, SZ, P]),
+    "stinet_f16_amax": (I, [P, I64, I64, I64, P, P]),
+    "stinet_f16_split": (I, [P, I64, I64, I64, P, P, P, I64, P, P]),
+    "stinet_linear_fwd_f16": (I, [P, P, I64, P, P, P, I64, P, P, P, P, I64, I64, I64, I64, I, P, SZ, P]),
+    "stinet_linear_dgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, I64, I64, I64, I, P, SZ, P]),
+    "stinet_linear_wgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, I64, I64, I64, I, P, SZ, P]),
+    "stinet_colsum": (I, [P, I64, P, I64, I64, P, P, SZ, P]),
 }
 
 REDUCE = {"add": 0, "sum": 0, "mean": 1, "max": 2}
-PREC = {"fp32": 0, "bf16": 1, "fp32_simt": 2, "tf32": 3, "bf16x3": 4}
+PREC = {"fp32": 0, "bf16": 1, "fp32_simt": 2, "tf32": 3, "bf16x3": 4, "fp32_tf32x3": 0}
+# arithmetic modes that run on fp16 operand planes (stinet_linear_*_f16): name -> tcgen05 passes per product
+PLANE_PASSES = {"fp32": 3, "f16": 1}
 ACT_NONE, ACT_ELU = 0, 1
 
 

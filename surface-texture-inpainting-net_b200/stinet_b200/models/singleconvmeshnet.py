@@ -60,7 +60,7 @@ class SingleConvMeshNet(torch.nn.Module):
         self.set_precision(precision)
 
     def set_precision(self, precision: str):
-        assert precision in ('fp32', 'bf16', 'bf16x3', 'fp32_simt', 'tf32')
+        assert precision in ('fp32', 'f16', 'bf16', 'bf16x3', 'fp32_simt', 'tf32', 'fp32_tf32x3')
         self.precision = precision
         for m in self.modules():
             if m is not self and hasattr(m, 'precision'):

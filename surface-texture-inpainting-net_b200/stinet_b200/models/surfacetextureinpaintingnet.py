@@ -160,7 +160,7 @@ class SurfaceTextureInpaintingNet(nn.Module):
         """Arithmetic of the dense layers: 'fp32' (tcgen05 3xTF32, fp32-class: reference parity 1e-5), 'bf16x3' (tcgen05
         bf16 tiles on hi/lo-split operands, fp32 accumulate: whole-network parity well inside 2e-2), 'bf16' (one bf16
         pass: 2e-2 per operator), 'tf32' (one TF32 pass) or 'fp32_simt' (FFMA cross-check)."""
-        assert precision in ('fp32', 'bf16', 'bf16x3', 'fp32_simt', 'tf32')
+        assert precision in ('fp32', 'f16', 'bf16', 'bf16x3', 'fp32_simt', 'tf32', 'fp32_tf32x3')
         self.precision = precision
         for m in self.modules():
             if m is not self and hasattr(m, 'precision'):
@@ -169,7 +169,7 @@ class SurfaceTextureInpaintingNet(nn.Module):
         # tiny (K = input_nc, N = output_nc) and HBM-bound, so this is free, and the hoisted first layer needs it:
         # W(x_j - x_i) is evaluated as Q_j - Q_i, and neighbouring vertices have nearly equal positions, so rounding
         # Q to 8 (bf16) or 10 (tf32) mantissa bits before the subtraction loses most of the difference.
-        self.io_precision = 'fp32' if precision in ('bf16', 'bf16x3', 'tf32') else precision
+        self.io_precision = 'fp32' if precision in ('f16', 'bf16', 'bf16x3', 'tf32') else precision
         for m in self.input_blocks.modules():
             if hasattr(m, 'precision'):
                 m.precision = self.io_precision

@@ -47,6 +47,113 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 # dense layers
 
 
+class Planes:
+    """fp16 hi / lo planes of a scaled fp32 matrix and the device scalar exp = -s (include/stinet_b200.h, "operand
+    PLANES").  Produced once per matrix and shared by every dense layer that reads it (fwd + wgrad for activations,
+    dgrad + wgrad for output gradients, fwd + dgrad for weights)."""
+    __slots__ = ("hi", "lo", "exp", "rows", "cols", "ld")
+
+    def __init__(self, hi, lo, exp, rows, cols, ld):
+        self.hi, self.lo, self.exp, self.rows, self.cols, self.ld = hi, lo, exp, rows, cols, ld
+
+
+_plane_epoch = 0
+
+
+def invalidate_planes() -> None:
+    """Forget every cached plane set (called before a CUDA-graph capture: a graph must contain the split kernels of
+    everything it reads, it may not lean on planes computed outside of it)."""
+    global _plane_epoch
+    _plane_epoch += 1
+
+
+def set_amax(t: torch.Tensor, amax: torch.Tensor) -> torch.Tensor:
+    """A producer kernel already knows max|t| (or an upper bound): planes_of(t) then skips its reduction pass."""
+    t._stinet_amax = (t._version, amax)
+    return t
+
+
+def planes_of(t: torch.Tensor, need_lo: bool = True) -> Planes:
+    """The operand planes of fp32 matrix `t`, cached on the tensor object (keyed by its version counter)."""
+    cached = getattr(t, "_stinet_planes", None)
+    if cached is not None and cached[0] == t._version and cached[1] == _plane_epoch and (cached[2].lo is not None or not need_lo):
+        return cached[2]
+    x = _mat(t)
+    rows, cols = x.shape
+    dev = x.device
+    s = _stream()
+    known = getattr(t, "_stinet_amax", None)
+    if known is not None and known[0] == t._version:
+        amax = known[1]
+    else:
+        amax = torch.empty(1, dtype=torch.float32, device=dev)
+        _abi.call("stinet_f16_amax", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), s,
+                  cost=(4 * rows * cols, 0, ""))
+    ld = (cols + 7) & ~7
+    hi = torch.empty((rows, ld), dtype=torch.float16, device=dev)
+    lo = torch.empty((rows, ld), dtype=torch.float16, device=dev) if need_lo else None
+    exp = torch.empty(1, dtype=torch.int32, device=dev)
+    _abi.call("stinet_f16_split", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), hi.data_ptr(), _ptr(lo), ld,
+              exp.data_ptr(), s, cost=(rows * cols * (4 + (4 if need_lo else 2)), 0, ""))
+    p = Planes(hi, lo, exp, rows, cols, ld)
+    t._stinet_planes = (t._version, _plane_epoch, p)
+    return p
+
+
+class LinearPlanesFn(Function):
+    """y = x W^T + b on fp16 operand planes (tcgen05 kind::f16; passes = 3: fp32-class result, 1: 11-bit operands)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, rowmask, passes):
+        need_lo = passes == 3
+        xp, wp = planes_of(x, need_lo), planes_of(weight, need_lo)
+        M, K = xp.rows, xp.cols
+        N = wp.rows
+        assert wp.cols == K
+        dev = xp.hi.device
+        y = torch.empty((M, N), dtype=torch.float32, device=dev)
+        nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
+        ws = _ws(nb, dev)
+        _abi.call("stinet_linear_fwd_f16", xp.hi.data_ptr(), _ptr(xp.lo), xp.ld, xp.exp.data_ptr(), wp.hi.data_ptr(),
+                  _ptr(wp.lo), wp.ld, wp.exp.data_ptr(), _ptr(bias), _ptr(rowmask), y.data_ptr(), N, M, N, K, passes,
+                  ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+        ctx.xp, ctx.wp, ctx.rowmask = xp, wp, rowmask
+        ctx.has_bias, ctx.passes = bias is not None, passes
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xp, wp, rowmask, passes = ctx.xp, ctx.wp, ctx.rowmask, ctx.passes
+        M, K, N = xp.rows, xp.cols, wp.rows
+        dev = xp.hi.device
+        dyp = planes_of(dy, passes == 3)
+        nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
+        ws = _ws(nb, dev)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.float32, device=dev)
+            _abi.call("stinet_linear_dgrad_f16", dyp.hi.data_ptr(), _ptr(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
+                      wp.hi.data_ptr(), _ptr(wp.lo), wp.ld, wp.exp.data_ptr(), dx.data_ptr(), K, M, N, K, passes,
+                      ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((N, K), dtype=torch.float32, device=dev)
+            if M > 0:
+                _abi.call("stinet_linear_wgrad_f16", dyp.hi.data_ptr(), _ptr(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
+                          xp.hi.data_ptr(), _ptr(xp.lo), xp.ld, xp.exp.data_ptr(), dw.data_ptr(), K, M, N, K, passes,
+                          ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+            else:
+                dw.zero_()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dym = _mat(dy)
+            db = torch.empty((N,), dtype=torch.float32, device=dev)
+            nbc = _abi.query("stinet_gemm_workspace_bytes", M, N, 1, 0)
+            wsc = _ws(nbc, dev)
+            _abi.call("stinet_colsum", dym.data_ptr(), _ld(dym), _ptr(rowmask), M, N, db.data_ptr(), wsc.data_ptr(), nbc,
+                      _stream(), cost=(4 * M * N, 0, f"N{N}"))
+        return dx, dw, db, None, None
+
+
 class LinearFn(Function):
     """y = x W^T + b, bias only on rows with rowmask > 0 when a rowmask is given."""
 
@@ -98,14 +205,17 @@ def linear(x, weight, bias=None, rowmask=None, precision="fp32"):
     are exact zeros and the extra output columns are sliced away again."""
     k, n = x.shape[1], weight.shape[0]
     pk, pn = (-k) % 4, (-n) % 4
+    passes = _abi.PLANE_PASSES.get(precision)
+    fn = LinearFn if passes is None else LinearPlanesFn
+    arg = precision if passes is None else passes
     if not (pk or pn):
-        return LinearFn.apply(x, weight, bias, rowmask, precision)
+        return fn.apply(x, weight, bias, rowmask, arg)
     if pk:
         x = torch.nn.functional.pad(x, (0, pk))
     weight = torch.nn.functional.pad(weight, (0, pk, 0, pn))
     if bias is not None and pn:
         bias = torch.nn.functional.pad(bias, (0, pn))
-    y = LinearFn.apply(x, weight, bias, rowmask, precision)
+    y = fn.apply(x, weight, bias, rowmask, arg)
     return y[:, :n] if pn else y
 
 
