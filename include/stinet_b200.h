@@ -182,7 +182,9 @@ int stinet_segnorm_stats(const float* x, int64_t ldx, int64_t n_rows, int64_t ch
 int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
                        int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, float eps,
                        const float* residual, int64_t ldr, int act, float* out, int64_t ldo, float* mean, float* rstd,
-                       void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+                       float* amax_out, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+/* amax_out (nullable, float[1], here and in stinet_segnorm_bwd): the kernels also leave max|out| (max|dx|) there -- the
+ * plane scale of the dense layer that reads the result next (stinet_f16_split) -- at no extra pass over the data. */
 /* out = residual + act((x - mean[g]) * rstd[g])   (residual nullable; act = STINET_ACT_*): the tail of
  * GraphResnetBlock.forward, models/surfacetextureinpaintingnet.py:510-521.  g = gid[r] (NULL: segment 0);
  * mean == rstd == NULL: identity norm (norm_type 'none', :257-263). */
@@ -196,7 +198,7 @@ int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows, int64_t ch
 int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows, int64_t channels,
                        int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt,
                        const int32_t* gid, const float* mean, const float* rstd, int act, float* dx, int64_t lddx,
-                       void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+                       float* amax_out, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
 
 /* ---- dense layers (replace torch.nn.Linear inside the message MLP, the shortcut and the head:
  * models/modules/edge_conv_filter.py:46-55, models/surfacetextureinpaintingnet.py:504-505,356-358).
@@ -232,14 +234,16 @@ int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t ld
 int stinet_f16_amax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* amax, stinet_stream_t stream);
 int stinet_f16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* amax, void* hi, void* lo,
                      int64_t ldp, int32_t* exp_out, stinet_stream_t stream);
-/* workspace for the three calls below: stinet_gemm_workspace_bytes(M, N, K, STINET_PREC_FP32) */
+/* workspace for the three calls below: stinet_gemm_workspace_bytes(M, N, K, STINET_PREC_FP32).
+ * amax_out (nullable, float[1]): the GEMM's epilogue also leaves max|C| (C, dA after bias) there, so that the consumer of
+ * the result can pick its plane scale without another pass over it. */
 int stinet_linear_fwd_f16(const void* A_hi, const void* A_lo, int64_t lda, const int32_t* a_exp, const void* W_hi,
                           const void* W_lo, int64_t ldw, const int32_t* w_exp, const float* bias,
-                          const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int passes,
-                          void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+                          const int32_t* rowmask, float* C, int64_t ldc, float* amax_out, int64_t M, int64_t N, int64_t K,
+                          int passes, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
 int stinet_linear_dgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* W_hi,
-                            const void* W_lo, int64_t ldw, const int32_t* w_exp, float* dA, int64_t lda, int64_t M,
-                            int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
+                            const void* W_lo, int64_t ldw, const int32_t* w_exp, float* dA, int64_t lda, float* amax_out,
+                            int64_t M, int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
                             stinet_stream_t stream);
 int stinet_linear_wgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* A_hi,
                             const void* A_lo, int64_t lda, const int32_t* a_exp, float* dW, int64_t ldw, int64_t M,
@@ -247,6 +251,28 @@ int stinet_linear_wgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, c
                             stinet_stream_t stream);
 int stinet_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int64_t M, int64_t N, float* dbias,
                   void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+
+/* colsum over a matrix held as planes: out[n] = sum_m x[m,n]  (workspace as stinet_colsum) */
+int stinet_colsum_planes(const void* hi, const void* lo, int64_t ldp, const int32_t* exp, int64_t M, int64_t N, float* out,
+                         void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+
+/* ---- fused EdgeConv message stage on operand planes (same reference call sites as stinet_edge_message_*): the hidden
+ * activations hid and the gradient dPQ = [dP | dQ] are only ever read by tensor-core GEMMs, so these variants write their
+ * fp16 planes directly (no fp32 matrix, no split pass).  The plane scale comes from an upper bound of the result that is
+ * known before the first element is written:  0 <= hid <= 2 max|PQ|  (pq_amax: the producing GEMM's amax_out) and
+ * |dPQ| <= max|dhid| * max(1, dq_factor)  (dhid_amax: the dgrad GEMM's amax_out; dq_factor = max_j sum_{j->i} 1/deg_i, a
+ * property of the edge set computed once by stinet_csr_dq_factor).  mask as in stinet_edge_message_fwd_mask (NULL in
+ * fwd_planes: inference, no decisions stored).  dpq planes are [n_rows, 2*hidden] with pitch ldp. */
+int stinet_csr_dq_factor(const int32_t* rowptr_t, const int32_t* rowptr_s, const int32_t* col_s, int64_t n, float* out,
+                         stinet_stream_t stream);
+int stinet_edge_message_fwd_planes(const float* P, int64_t ldp, const float* Q, int64_t ldq, const int32_t* rowptr_t,
+                                   const int32_t* col_t, int64_t n_rows, int64_t hidden, const float* pq_amax,
+                                   void* hid_hi, void* hid_lo, int64_t ldh, int32_t* hid_exp, void* mask,
+                                   stinet_stream_t stream);
+int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* dhid_amax, const float* dq_factor,
+                                   const int32_t* rowptr_t, const int32_t* rowptr_s, const int32_t* col_s,
+                                   const int32_t* tpos_s, const void* mask, int64_t n_rows, int64_t hidden, void* dpq_hi,
+                                   void* dpq_lo, int64_t ldp, int32_t* dpq_exp, stinet_stream_t stream);
 
 /* ---- per-step graph metrics (replace utils/metrics/graph_metrics.py:6-72 as called from
  * trainers/inpainting3d_trainer.py:254-263) on the level-0 CSR by target.  Scalar results are written to `out` on the

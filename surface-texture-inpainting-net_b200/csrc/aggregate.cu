@@ -386,6 +386,160 @@ edge_message_bwd_source_mask_kernel(const float* __restrict__ dhid, int64_t ldd,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same three kernels writing fp16 operand PLANES instead of fp32 (include/stinet_b200.h, "dense layers on operand
+// PLANES"): hid and dPQ are read by nothing but tensor-core GEMMs, so they never exist as fp32 matrices.  The plane
+// scale needs max|result| BEFORE the first element is written; both have cheap upper bounds from a number the producing
+// GEMM's epilogue already knows:
+//     0 <= hid  = mean relu(P_i + Q_j)            <= 2 max|PQ|
+//     |dP_i|   <= |dhid_i|,   |dQ_j| <= sum_{j->i} |dhid_i| / deg_i  <= max|dhid| * dq_factor,
+//     dq_factor = max_j sum_{j->i} 1/deg_i   (a property of the edge set: stinet_csr_dq_factor)
+// A bound within 2^16 of the true maximum costs no accuracy (22-bit planes, fp16 exponent range).
+
+template <bool MASK>
+__global__ void __launch_bounds__(kAggThreads)
+edge_message_fwd_planes_kernel(const float* __restrict__ P, int64_t ldp, const float* __restrict__ Q, int64_t ldq,
+                               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+                               int hidden, const unsigned* __restrict__ pq_amax, __half* __restrict__ hi,
+                               __half* __restrict__ lo, int64_t ldh, int32_t* __restrict__ exp_out,
+                               uint8_t* __restrict__ mask) {
+  const int sft = plane_shift(__float_as_uint(2.f * __uint_as_float(__ldg(pq_amax))));
+  const float scale = plane_scale(sft);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = -sft;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  const int c4n = hidden >> 2;
+  const int nchunk = (c4n + 31) >> 5;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t i = it / nchunk;
+    const int chunk = (int)(it - i * nchunk);
+    const int c4 = chunk * 32 + lane;
+    if (c4 >= c4n) continue;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const float den = (float)max(end - beg, 1);
+    const float4 p = reinterpret_cast<const float4*>(P + i * ldp)[c4];
+    uint8_t* __restrict__ mrow = mask + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = beg;
+    for (; k + 4 <= end; k += 4) {
+      int j[4];
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) j[u] = col[k + u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = reinterpret_cast<const float4*>(Q + (int64_t)j[u] * ldq)[c4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float sx = p.x + q[u].x, sy = p.y + q[u].y, sz = p.z + q[u].z, sw = p.w + q[u].w;
+        acc.x += relu(sx); acc.y += relu(sy); acc.z += relu(sz); acc.w += relu(sw);
+        if (MASK) mrow[(int64_t)(k + u) * c4n] = (uint8_t)nibble(sx, sy, sz, sw);
+      }
+    }
+    for (; k < end; ++k) {
+      const float4 q = reinterpret_cast<const float4*>(Q + (int64_t)col[k] * ldq)[c4];
+      const float sx = p.x + q.x, sy = p.y + q.y, sz = p.z + q.z, sw = p.w + q.w;
+      acc.x += relu(sx); acc.y += relu(sy); acc.z += relu(sz); acc.w += relu(sw);
+      if (MASK) mrow[(int64_t)k * c4n] = (uint8_t)nibble(sx, sy, sz, sw);
+    }
+    split_store4(f4_div(acc, den), scale, hi + i * ldh + 4 * c4, lo != nullptr ? lo + i * ldh + 4 * c4 : nullptr);
+  }
+}
+
+// the plane scale of dPQ = [dP | dQ] from max|dhid| and the edge set's dq_factor; both backward kernels derive the same
+__device__ __forceinline__ int dpq_shift(const unsigned* dhid_amax, const float* dq_factor) {
+  return plane_shift(__float_as_uint(__uint_as_float(__ldg(dhid_amax)) * fmaxf(1.f, __ldg(dq_factor))));
+}
+
+__global__ void __launch_bounds__(kAggThreads)
+edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr,
+                                      const uint8_t* __restrict__ mask, int64_t n_rows, int hidden,
+                                      const unsigned* __restrict__ dhid_amax, const float* __restrict__ dq_factor,
+                                      __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
+                                      int32_t* __restrict__ exp_out) {
+  const int sft = dpq_shift(dhid_amax, dq_factor);
+  const float scale = plane_scale(sft);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = -sft;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  const int c4n = hidden >> 2;
+  const int nchunk = (c4n + 31) >> 5;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t i = it / nchunk;
+    const int chunk = (int)(it - i * nchunk);
+    const int c4 = chunk * 32 + lane;
+    if (c4 >= c4n) continue;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const float den = (float)max(end - beg, 1);
+    const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + i * ldd)[c4], den);
+    const uint8_t* __restrict__ mrow = mask + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = beg; k < end; ++k) {
+      const unsigned m = __ldg(mrow + (int64_t)k * c4n);
+      acc.x += (m & 1u) ? d.x : 0.f;
+      acc.y += (m & 2u) ? d.y : 0.f;
+      acc.z += (m & 4u) ? d.z : 0.f;
+      acc.w += (m & 8u) ? d.w : 0.f;
+    }
+    split_store4(acc, scale, hi + i * ldp + 4 * c4, lo != nullptr ? lo + i * ldp + 4 * c4 : nullptr);
+  }
+}
+
+__global__ void __launch_bounds__(kAggThreads)
+edge_message_bwd_source_planes_kernel(const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr_t,
+                                      const int32_t* __restrict__ rowptr_s, const int32_t* __restrict__ col_s,
+                                      const int32_t* __restrict__ tpos_s, const uint8_t* __restrict__ mask,
+                                      int64_t n_rows, int hidden, const unsigned* __restrict__ dhid_amax,
+                                      const float* __restrict__ dq_factor, __half* __restrict__ hi,
+                                      __half* __restrict__ lo, int64_t ldp) {
+  const float scale = plane_scale(dpq_shift(dhid_amax, dq_factor));
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
+  const int c4n = hidden >> 2;
+  const int nchunk = (c4n + 31) >> 5;
+  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
+    const int64_t j = it / nchunk;
+    const int chunk = (int)(it - j * nchunk);
+    const int c4 = chunk * 32 + lane;
+    if (c4 >= c4n) continue;
+    const int beg = rowptr_s[j], end = rowptr_s[j + 1];
+    const uint8_t* __restrict__ mrow = mask + c4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = beg; k < end; ++k) {
+      const int i = col_s[k];
+      const float den = (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
+      const unsigned m = __ldg(mrow + (int64_t)tpos_s[k] * c4n);
+      const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + (int64_t)i * ldd)[c4], den);
+      acc.x += (m & 1u) ? d.x : 0.f;
+      acc.y += (m & 2u) ? d.y : 0.f;
+      acc.z += (m & 4u) ? d.z : 0.f;
+      acc.w += (m & 8u) ? d.w : 0.f;
+    }
+    split_store4(acc, scale, hi + j * ldp + 4 * c4, lo != nullptr ? lo + j * ldp + 4 * c4 : nullptr);
+  }
+}
+
+// dq_factor = max over vertices j of  sum over out-edges (j -> i) of 1 / max(deg_i, 1)   (>= 0; one thread per vertex)
+__global__ void __launch_bounds__(256) csr_dq_factor_kernel(const int32_t* __restrict__ rowptr_t,
+                                                            const int32_t* __restrict__ rowptr_s,
+                                                            const int32_t* __restrict__ col_s, int64_t n,
+                                                            unsigned* __restrict__ out) {
+  float f = 0.f;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int k = rowptr_s[j]; k < rowptr_s[j + 1]; ++k) {
+      const int i = col_s[k];
+      t += 1.f / (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
+    }
+    f = fmaxf(f, t);
+  }
+  amax_publish(__float_as_uint(f), out);
+}
+
 inline bool vec_ok(int64_t channels, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
   if (channels & 3) return false;
   for (auto p : ptrs)
@@ -566,4 +720,64 @@ extern "C" int stinet_edge_message_bwd_source_mask(const float* dhid, int64_t ld
   K(edge_message_bwd_source_mask_kernel<<<row_grid(n_rows, hidden, true), kAggThreads, 0, s>>>(
       dhid, ldd, rowptr_t, rowptr_s, col_s, tpos_s, static_cast<const uint8_t*>(mask), n_rows, (int)hidden, dQ, lddq));
   return check_launch("edge_message_bwd_source_mask");
+}
+
+extern "C" int stinet_csr_dq_factor(const int32_t* rowptr_t, const int32_t* rowptr_s, const int32_t* col_s, int64_t n,
+                                    float* out, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(rowptr_t && rowptr_s && out, STINET_ERR_ARG, "csr_dq_factor: null pointer");
+  STINET_REQUIRE(n >= 0, STINET_ERR_ARG, "csr_dq_factor: bad shape");
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), s);
+  STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "csr_dq_factor: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (n == 0) return STINET_OK;
+  K(csr_dq_factor_kernel<<<wave_grid(n, 256, 8), 256, 0, s>>>(rowptr_t, rowptr_s, col_s, n, reinterpret_cast<unsigned*>(out)));
+  return check_launch("csr_dq_factor");
+}
+
+static bool planes_ok(int64_t hidden, const void* hi, const void* lo, int64_t ld) {
+  return !(hidden & 3) && !(ld & 7) && ld >= hidden && aligned16(hi) && (lo == nullptr || aligned16(lo));
+}
+
+extern "C" int stinet_edge_message_fwd_planes(const float* P, int64_t ldp, const float* Q, int64_t ldq,
+                                              const int32_t* rowptr_t, const int32_t* col_t, int64_t n_rows,
+                                              int64_t hidden, const float* pq_amax, void* hid_hi, void* hid_lo,
+                                              int64_t ldh, int32_t* hid_exp, void* mask, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(P && Q && rowptr_t && pq_amax && hid_hi && hid_exp, STINET_ERR_ARG, "edge_message_fwd_planes: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldp >= hidden && ldq >= hidden, STINET_ERR_ARG, "edge_message_fwd_planes: bad shape");
+  STINET_REQUIRE(vec_ok(hidden, {P, Q}, {ldp, ldq}) && planes_ok(hidden, hid_hi, hid_lo, ldh), STINET_ERR_UNSUPPORTED,
+                 "edge_message_fwd_planes: needs hidden %% 4 == 0, 16-byte aligned rows, plane pitch %% 8 == 0");
+  const int g = n_rows > 0 ? row_grid(n_rows, hidden, true) : 1;      // n_rows == 0 still publishes the exponent
+  const unsigned* am = reinterpret_cast<const unsigned*>(pq_amax);
+  if (mask != nullptr)
+    K(edge_message_fwd_planes_kernel<true><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, rowptr_t, col_t, n_rows, (int)hidden, am,
+        static_cast<__half*>(hid_hi), static_cast<__half*>(hid_lo), ldh, hid_exp, static_cast<uint8_t*>(mask)));
+  else
+    K(edge_message_fwd_planes_kernel<false><<<g, kAggThreads, 0, s>>>(P, ldp, Q, ldq, rowptr_t, col_t, n_rows, (int)hidden, am,
+        static_cast<__half*>(hid_hi), static_cast<__half*>(hid_lo), ldh, hid_exp, nullptr));
+  return check_launch("edge_message_fwd_planes");
+}
+
+extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* dhid_amax,
+                                              const float* dq_factor, const int32_t* rowptr_t,
+                                              const int32_t* rowptr_s, const int32_t* col_s, const int32_t* tpos_s,
+                                              const void* mask, int64_t n_rows, int64_t hidden, void* dpq_hi,
+                                              void* dpq_lo, int64_t ldp, int32_t* dpq_exp, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(dhid && dhid_amax && dq_factor && rowptr_t && rowptr_s && tpos_s && mask && dpq_hi && dpq_exp, STINET_ERR_ARG,
+                 "edge_message_bwd_planes: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && hidden > 0 && ldd >= hidden && ldp >= 2 * hidden, STINET_ERR_ARG, "edge_message_bwd_planes: bad shape");
+  STINET_REQUIRE(vec_ok(hidden, {dhid}, {ldd}) && planes_ok(2 * hidden, dpq_hi, dpq_lo, ldp), STINET_ERR_UNSUPPORTED,
+                 "edge_message_bwd_planes: needs hidden %% 4 == 0, 16-byte aligned rows, plane pitch %% 8 == 0");
+  const int g = n_rows > 0 ? row_grid(n_rows, hidden, true) : 1;
+  const unsigned* am = reinterpret_cast<const unsigned*>(dhid_amax);
+  __half* hi = static_cast<__half*>(dpq_hi);
+  __half* lo = static_cast<__half*>(dpq_lo);
+  K(edge_message_bwd_target_planes_kernel<<<g, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask), n_rows,
+                                                                   (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp));
+  if (n_rows > 0)
+    K(edge_message_bwd_source_planes_kernel<<<g, kAggThreads, 0, s>>>(
+        dhid, ldd, rowptr_t, rowptr_s, col_s, tpos_s, static_cast<const uint8_t*>(mask), n_rows, (int)hidden, am, dq_factor,
+        hi + hidden, lo != nullptr ? lo + hidden : nullptr, ldp));
+  return check_launch("edge_message_bwd_planes");
 }

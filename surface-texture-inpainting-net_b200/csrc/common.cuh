@@ -1,5 +1,6 @@
 // Shared helpers for the stinet_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -62,6 +63,43 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w));
+}
+
+// ---- fp16 operand planes of the dense layers (include/stinet_b200.h, "dense layers on operand PLANES")
+// s with bound 2^s in [2^14, 2^15) (bound = 0, inf or NaN: s = 0), clamped so that 2^s and 2^-s stay normal floats;
+// `bound_bits` is the fp32 bit pattern of max|x| or of any upper bound of it
+__device__ __forceinline__ int plane_shift(unsigned bound_bits) {
+  const int e = (int)((bound_bits >> 23) & 0xFFu);
+  if ((bound_bits & 0x7FFFFFFFu) == 0u || e == 255) return 0;
+  const int s = 15 - (max(e, 1) - 126);
+  return max(-110, min(110, s));
+}
+__device__ __forceinline__ float plane_scale(int shift) { return __uint_as_float((uint32_t)(127 + shift) << 23); }
+// hi = fp16(x 2^s), lo = fp16((x 2^s - hi) 2^11)
+__device__ __forceinline__ void split_one(float x, float scale, __half& hi, __half& lo) {
+  const float xs = x * scale;
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn((xs - __half2float(hi)) * 2048.f);
+}
+// four consecutive elements -> 8 bytes of each plane
+__device__ __forceinline__ void split_store4(float4 v, float scale, __half* hi, __half* lo) {
+  __half h[4], l[4];
+  split_one(v.x, scale, h[0], l[0]); split_one(v.y, scale, h[1], l[1]);
+  split_one(v.z, scale, h[2], l[2]); split_one(v.w, scale, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<const uint2*>(h);
+  if (lo != nullptr) *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
+}
+// the value a plane pair stands for, still scaled by 2^s
+__device__ __forceinline__ float plane_value(__half hi, __half lo) { return __half2float(hi) + __half2float(lo) * (1.f / 2048.f); }
+// max |v| of a float4 folded into a running bit-pattern maximum
+__device__ __forceinline__ unsigned amax4(unsigned m, float4 v) {
+  m = max(max(m, __float_as_uint(v.x) & 0x7FFFFFFFu), __float_as_uint(v.y) & 0x7FFFFFFFu);
+  return max(max(m, __float_as_uint(v.z) & 0x7FFFFFFFu), __float_as_uint(v.w) & 0x7FFFFFFFu);
+}
+// one atomicMax per warp, skipped when the warp cannot raise the value (a stale read can only under-estimate it)
+__device__ __forceinline__ void amax_publish(unsigned m, unsigned* slot) {
+  m = __reduce_max_sync(0xFFFFFFFFu, m);
+  if ((threadIdx.x & 31) == 0 && m > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(slot, m);
 }
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }

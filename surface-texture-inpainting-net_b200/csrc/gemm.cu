@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(GemmArgs g) {
 // fixed-order sum of the split partials (+ bias on rows with rowmask > 0): deterministic second stage of a split GEMM
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t IJ, int J,
                                      float* __restrict__ out, int64_t ldo, const float* __restrict__ bias,
-                                     const int32_t* __restrict__ rowmask) {
+                                     const int32_t* __restrict__ rowmask, unsigned* __restrict__ amax_out = nullptr) {
+  unsigned m = 0u;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < IJ;
        idx += (int64_t)gridDim.x * blockDim.x) {
     float t = 0.f;
@@ -179,6 +180,11 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
     const int j = (int)(idx - i * J);
     if (bias != nullptr && (rowmask == nullptr || rowmask[i] > 0)) t += bias[j];
     out[i * ldo + j] = t;
+    m = max(m, __float_as_uint(t) & 0x7FFFFFFFu);
+  }
+  if (amax_out != nullptr) {   // max |out| as a bit pattern (one atomic per warp that can raise it)
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0 && m > *reinterpret_cast<volatile unsigned*>(amax_out)) atomicMax(amax_out, m);
   }
 }
 
@@ -324,6 +330,66 @@ static void run_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int
   K(colsum_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(part, chunks, (int)N, dbias));
 }
 
+// column sums of a matrix given as operand planes (dbias of the hoisted first layer: dP exists as planes only):
+// stage 1 as colsum_partial_vec_kernel on plane values (still scaled by 2^s), stage 2 applies 2^exp.
+__global__ void __launch_bounds__(256) colsum_planes_partial_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                                    int64_t ldp, int64_t M, int N, int rows_per_chunk,
+                                                                    float* __restrict__ part) {
+  constexpr int CL = 32, RL = 8;
+  __shared__ float4 sm[RL][CL];
+  const int tx = threadIdx.x % CL, ty = threadIdx.x / CL;
+  const int n0 = (blockIdx.x * CL + tx) * 4;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t m1 = min(M, m0 + rows_per_chunk);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n0 < N) {
+    for (int64_t m = m0 + ty; m < m1; m += 4 * RL) {
+      uint2 h[4], l[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t mm = m + u * RL;
+        h[u] = l[u] = make_uint2(0u, 0u);
+        if (mm < m1) {
+          h[u] = *reinterpret_cast<const uint2*>(hi + mm * ldp + n0);
+          if (lo != nullptr) l[u] = *reinterpret_cast<const uint2*>(lo + mm * ldp + n0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half* hh = reinterpret_cast<const __half*>(&h[u]);
+        const __half* ll = reinterpret_cast<const __half*>(&l[u]);
+        acc.x += plane_value(hh[0], ll[0]); acc.y += plane_value(hh[1], ll[1]);
+        acc.z += plane_value(hh[2], ll[2]); acc.w += plane_value(hh[3], ll[3]);
+      }
+    }
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n0 < N) {
+    float4 t = sm[0][tx];
+#pragma unroll
+    for (int y = 1; y < RL; ++y) { const float4 q = sm[y][tx]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+    *reinterpret_cast<float4*>(part + (int64_t)blockIdx.y * N + n0) = t;
+  }
+}
+__global__ void __launch_bounds__(1024) colsum_planes_final_kernel(const float* __restrict__ part, int chunks, int N,
+                                                                  const int32_t* __restrict__ exp, float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float t = 0.f;
+  if (n < N)
+    for (int c = ty; c < chunks; c += 32) t += part[(int64_t)c * N + n];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float r = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) r += sm[y][tx];
+    out[n] = ldexpf(r, __ldg(exp));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // operand planes for the fp16 tensor-core modes (see include/stinet_b200.h, "dense layers on operand PLANES")
 
@@ -360,25 +426,12 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, 
   }
 }
 
-// s with amax 2^s in [2^14, 2^15) (amax = 0, inf or NaN: s = 0), clamped so that 2^s and 2^-s stay normal floats
-__device__ __forceinline__ int plane_shift(unsigned amax_bits) {
-  const int e = (int)((amax_bits >> 23) & 0xFFu);
-  if ((amax_bits & 0x7FFFFFFFu) == 0u || e == 255) return 0;
-  const int s = 15 - (max(e, 1) - 126);
-  return max(-110, min(110, s));
-}
-__device__ __forceinline__ void split_one(float x, float scale, __half& hi, __half& lo) {
-  const float xs = x * scale;
-  hi = __float2half_rn(xs);
-  lo = __float2half_rn((xs - __half2float(hi)) * 2048.f);
-}
-
 // x [rows, cols] fp32 -> hi / lo fp16 planes (pitch ldp) of x 2^s; exp_out = -s.  Vector form: 8 elements per thread.
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols,
                                                         const unsigned* __restrict__ amax, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, int64_t ldp, int32_t* __restrict__ exp_out) {
   const int sft = plane_shift(__ldg(amax));
-  const float scale = __uint_as_float((uint32_t)(127 + sft) << 23);
+  const float scale = plane_scale(sft);
   if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = -sft;
   if ((cols & 7) == 0 && (ldx & 3) == 0 && aligned16(x)) {
     const int cpr = cols >> 3;
@@ -803,7 +856,12 @@ static int f16_mode(int passes) { return passes == 3 ? tc::MODE_F16X3 : passes =
 
 // one planes GEMM  C[I,J] = sum_t A'(i,t) B'(t,j) 2^(a_exp + b_exp), split over t when the tiles do not fill the SMs
 static int run_planes(tc::Problem p, int max_splits, const float* bias, const int32_t* rowmask, float* C, int64_t ldc,
-                      const GemmWs& w, bool have_ws, const char* what, cudaStream_t s) {
+                      float* amax_out, const GemmWs& w, bool have_ws, const char* what, cudaStream_t s) {
+  unsigned* amax_bits = reinterpret_cast<unsigned*>(amax_out);
+  if (amax_bits != nullptr) {
+    cudaError_t e = cudaMemsetAsync(amax_bits, 0, sizeof(unsigned), s);
+    STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "%s: cudaMemsetAsync: %s", what, cudaGetErrorString(e));
+  }
   STINET_REQUIRE(tc::eligible(p), STINET_ERR_UNSUPPORTED,
                  "%s: operand planes / output not addressable by TMA (16-byte pitches, output width %% 4)", what);
   const TcSplit sp = tc_split(p.I, p.J, p.T, max_splits);
@@ -813,20 +871,21 @@ static int run_planes(tc::Problem p, int max_splits, const float* bias, const in
     int rc = tc::run(p, s);
     if (rc) return rc;
     const int64_t IJ = p.I * p.J;
-    if (sp.splits >= 16 && bias == nullptr && !(p.J & 3) && !(ldc & 3) && aligned16(C))
+    if (sp.splits >= 16 && bias == nullptr && amax_bits == nullptr && !(p.J & 3) && !(ldc & 3) && aligned16(C))
       K(splitk_reduce_wide_kernel<<<(unsigned)ceil_div(IJ, 128), 256, 0, s>>>(w.splitk, sp.splits, IJ, (int)p.J, C, ldc));
     else
-      K(splitk_reduce_kernel<<<wave_grid(IJ, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, IJ, (int)p.J, C, ldc, bias, rowmask));
+      K(splitk_reduce_kernel<<<wave_grid(IJ, 256, 8), 256, 0, s>>>(w.splitk, sp.splits, IJ, (int)p.J, C, ldc, bias, rowmask,
+                                                                   amax_bits));
     return check_launch(what);
   }
-  p.C = C; p.ldc = ldc; p.bias = bias; p.rowmask = rowmask; p.splits = 1; p.t_per_split = p.T;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.rowmask = rowmask; p.splits = 1; p.t_per_split = p.T; p.amax_out = amax_bits;
   return tc::run(p, s);
 }
 
 extern "C" int stinet_linear_fwd_f16(const void* A_hi, const void* A_lo, int64_t lda, const int32_t* a_exp, const void* W_hi,
                                      const void* W_lo, int64_t ldw, const int32_t* w_exp, const float* bias,
-                                     const int32_t* rowmask, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                                     int passes, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+                                     const int32_t* rowmask, float* C, int64_t ldc, float* amax_out, int64_t M, int64_t N,
+                                     int64_t K, int passes, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const int mode = f16_mode(passes);
   STINET_REQUIRE(mode >= 0, STINET_ERR_ARG, "linear_fwd_f16: passes must be 1 or 3");
@@ -835,13 +894,13 @@ extern "C" int stinet_linear_fwd_f16(const void* A_hi, const void* A_lo, int64_t
   if (M == 0) return STINET_OK;
   GemmWs w = carve_gemm(workspace, M, N, K, STINET_PREC_FP32);
   tc::Problem p{A_hi, lda, false, W_hi, ldw, false, C, ldc, bias, rowmask, M, N, K, 1, K, mode, A_lo, W_lo, a_exp, w_exp};
-  return run_planes(p, kFwdMaxSplits, bias, rowmask, C, ldc, w, workspace && workspace_bytes >= w.bytes, "linear_fwd_f16", s);
+  return run_planes(p, kFwdMaxSplits, bias, rowmask, C, ldc, amax_out, w, workspace && workspace_bytes >= w.bytes, "linear_fwd_f16", s);
 }
 
 extern "C" int stinet_linear_dgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* W_hi,
-                                       const void* W_lo, int64_t ldw, const int32_t* w_exp, float* dA, int64_t lda, int64_t M,
-                                       int64_t N, int64_t K, int passes, void* workspace, size_t workspace_bytes,
-                                       stinet_stream_t stream_) {
+                                       const void* W_lo, int64_t ldw, const int32_t* w_exp, float* dA, int64_t lda,
+                                       float* amax_out, int64_t M, int64_t N, int64_t K, int passes, void* workspace,
+                                       size_t workspace_bytes, stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const int mode = f16_mode(passes);
   STINET_REQUIRE(mode >= 0, STINET_ERR_ARG, "linear_dgrad_f16: passes must be 1 or 3");
@@ -851,7 +910,7 @@ extern "C" int stinet_linear_dgrad_f16(const void* dC_hi, const void* dC_lo, int
   GemmWs w = carve_gemm(workspace, M, N, K, STINET_PREC_FP32);
   // dA[i=m, j=k] = sum_{t=n} dC[m,n] * W[n,k]
   tc::Problem p{dC_hi, ldc, false, W_hi, ldw, true, dA, lda, nullptr, nullptr, M, K, N, 1, N, mode, dC_lo, W_lo, c_exp, w_exp};
-  return run_planes(p, kFwdMaxSplits, nullptr, nullptr, dA, lda, w, workspace && workspace_bytes >= w.bytes, "linear_dgrad_f16", s);
+  return run_planes(p, kFwdMaxSplits, nullptr, nullptr, dA, lda, amax_out, w, workspace && workspace_bytes >= w.bytes, "linear_dgrad_f16", s);
 }
 
 extern "C" int stinet_linear_wgrad_f16(const void* dC_hi, const void* dC_lo, int64_t ldc, const int32_t* c_exp, const void* A_hi,
@@ -868,5 +927,24 @@ extern "C" int stinet_linear_wgrad_f16(const void* dC_hi, const void* dC_lo, int
                  workspace_bytes, w.bytes);
   // dW[i=n, j=k] = sum_{t=m} dC[m,n] * A[m,k]
   tc::Problem p{dC_hi, ldc, true, A_hi, lda, true, dW, ldw, nullptr, nullptr, N, K, M, 1, M, mode, dC_lo, A_lo, c_exp, a_exp};
-  return run_planes(p, kWgradMaxSplits, nullptr, nullptr, dW, ldw, w, true, "linear_wgrad_f16", s);
+  return run_planes(p, kWgradMaxSplits, nullptr, nullptr, dW, ldw, nullptr, w, true, "linear_wgrad_f16", s);
+}
+
+extern "C" int stinet_colsum_planes(const void* hi, const void* lo, int64_t ldp, const int32_t* exp, int64_t M, int64_t N,
+                                    float* out, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(hi && exp && out, STINET_ERR_ARG, "colsum_planes: null pointer");
+  STINET_REQUIRE(M >= 0 && N > 0 && N % 4 == 0 && ldp >= N && ldp % 4 == 0, STINET_ERR_ARG, "colsum_planes: bad shape");
+  STINET_REQUIRE((reinterpret_cast<uintptr_t>(hi) & 7u) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7u) == 0, STINET_ERR_ARG,
+                 "colsum_planes: planes must be 8-byte aligned");
+  GemmWs w = carve_gemm(workspace, M, N, 1, STINET_PREC_FP32);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "colsum_planes: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  const int rpc = colsum_rows(M > 0 ? M : 1, N);
+  const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
+  dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
+  K(colsum_planes_partial_kernel<<<g2, 256, 0, s>>>(static_cast<const __half*>(hi), static_cast<const __half*>(lo), ldp, M, (int)N,
+                                                   rpc, w.colsum));
+  K(colsum_planes_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(w.colsum, chunks, (int)N, exp, out));
+  return check_launch("colsum_planes");
 }

@@ -56,6 +56,7 @@ struct TcArgs {
   int split_acc;                   // fp32 mode: keep the hi*lo + lo*hi correction terms in their own TMEM accumulator
   const int32_t* a_exp;            // F16 modes: the result is multiplied by 2^(*a_exp + *b_exp) (operand plane scales)
   const int32_t* b_exp;
+  unsigned* amax_out;              // nullable: max |C| (after bias) as an fp32 bit pattern, atomicMax into a zeroed slot
 };
 
 #ifdef STINET_TC_DEBUG
@@ -511,6 +512,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < EC; ++c) acc[c] = acc[c] * f1 * f2;
       }
+      unsigned amax_bits = 0u;
       if (row0 < g.I) {
 #pragma unroll
         for (int cc = 0; cc < EC; cc += 32) {
@@ -525,12 +527,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float4 b = *reinterpret_cast<const float4*>(g.bias + jb + 4 * c4);
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
+            amax_bits = max(max(amax_bits, __float_as_uint(v.x) & 0x7FFFFFFFu), __float_as_uint(v.y) & 0x7FFFFFFFu);
+            amax_bits = max(max(amax_bits, __float_as_uint(v.z) & 0x7FFFFFFFu), __float_as_uint(v.w) & 0x7FFFFFFFu);
             stage[lane * 8 + (c4 ^ (lane & 7))] = v;       // the 128-byte swizzle of the tensor map, by hand
           }
           fence_proxy_async();                             // generic-proxy smem writes -> visible to the TMA unit
           __syncwarp();
           if (lane == 0) tma_store_3d(&tmC, smem_u32(stage), jb, row0, w.z);
         }
+      }
+      if (g.amax_out != nullptr) {
+        // rows / columns outside the matrix hold exact zeros (TMA zero fill, no bias), so they cannot raise the maximum
+        amax_bits = __reduce_max_sync(0xFFFFFFFFu, amax_bits);
+        if (lane == 0 && amax_bits > *reinterpret_cast<volatile unsigned*>(g.amax_out)) atomicMax(g.amax_out, amax_bits);
       }
       DBG_ADD(5);
     }
@@ -645,7 +654,7 @@ static int launch(const Problem& p, cudaStream_t s) {
   if (C_::kF16) STINET_REQUIRE(p.a_exp && p.b_exp, STINET_ERR_ARG, "gemm_tc: the fp16 modes need the operand scale exponents");
   TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split,
            tiles_j, tiles_i * tiles_j, (int)units,
-           promote, C_::kFp32 ? (C_::kF16 ? 1 : env_split) : 0, p.a_exp, p.b_exp};
+           promote, C_::kFp32 ? (C_::kF16 ? 1 : env_split) : 0, p.a_exp, p.b_exp, p.splits == 1 ? p.amax_out : nullptr};
   const unsigned grid = (unsigned)(units < kSMs ? units : kSMs);   // persistent: one CTA per SM walks the work units
   K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, tmC, g));
   return check_launch("gemm_tc");

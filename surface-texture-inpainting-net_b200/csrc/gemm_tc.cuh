@@ -31,6 +31,7 @@ struct Problem {
   const void* B_lo = nullptr;
   const int32_t* a_exp = nullptr;   // F16 modes: device scalars, result *= 2^(*a_exp + *b_exp)
   const int32_t* b_exp = nullptr;
+  unsigned* amax_out = nullptr;     // nullable, unsplit launches only: atomicMax of |C| bit patterns into a zeroed slot
 };
 
 bool eligible(const Problem& p);              // TMA alignment / size rules

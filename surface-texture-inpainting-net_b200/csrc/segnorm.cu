@@ -247,14 +247,15 @@ __global__ void __launch_bounds__(kNormThreads)
 segnorm_slice_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ aux, int64_t lda,
                            const int32_t* __restrict__ slice_ptr, int channels, const float* __restrict__ mean,
                            const float* __restrict__ rstd, const float* __restrict__ s1, const float* __restrict__ s2,
-                           int act, float* __restrict__ out, int64_t ldo) {
+                           int act, float* __restrict__ out, int64_t ldo, unsigned* __restrict__ amax_out) {
   const int groups = channels >> 2;
   const int txw = min(groups, kTileGroups);
   const int tyn = kNormThreads / txw;
   const int tx = threadIdx.x % txw, ty = threadIdx.x / txw;
   const int s = blockIdx.y;
   const int grp = blockIdx.z * kTileGroups + tx;
-  if (grp >= groups || ty >= tyn) return;
+  unsigned amax_bits = 0u;
+  if (grp < groups && ty < tyn) {
   const int rows_per_cta = tyn * kApplyU * 2;
   const int r0 = slice_ptr[s] + blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, slice_ptr[s + 1]);
@@ -297,10 +298,14 @@ segnorm_slice_apply_kernel(const float* __restrict__ x, int64_t ldx, const float
             if (aux) o[q] += wv[q];
           }
         }
-        st_stream(reinterpret_cast<float4*>(out + (int64_t)r * ldo) + grp, make_float4(o[0], o[1], o[2], o[3]));
+        const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+        amax_bits = amax4(amax_bits, ov);
+        st_stream(reinterpret_cast<float4*>(out + (int64_t)r * ldo) + grp, ov);
       }
     }
   }
+  }
+  if (amax_out != nullptr) amax_publish(amax_bits, amax_out);   // max |out| for the plane scale of the next dense layer
 }
 
 constexpr int kFusedG = 8;        // float4 columns per CTA: a 32-channel slab = one 128-byte line per row
@@ -316,6 +321,7 @@ struct FusedArgs {
   float* mean; float* rstd;            // fwd: outputs; bwd: inputs
   float* out; int64_t ldo;
   int channels; int act; float eps;
+  unsigned* amax_out;                  // nullable: max |out| as a bit pattern (atomicMax into a zeroed slot)
 };
 
 __device__ __forceinline__ float4 f4add(const float4& a, const float4& b) {
@@ -415,10 +421,12 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_fwd_kernel(FusedAr
     reinterpret_cast<float4*>(a.mean + (int64_t)s * a.channels)[c4] = m;
     reinterpret_cast<float4*>(a.rstd + (int64_t)s * a.channels)[c4] = rs;
   }
+  unsigned amax_bits = 0u;
   auto finish = [&](const float4& xv, int r) {
     float4 o = make_float4((xv.x - m.x) * rs.x, (xv.y - m.y) * rs.y, (xv.z - m.z) * rs.z, (xv.w - m.w) * rs.w);
     if (a.act == STINET_ACT_ELU) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
     if (a.aux) o = f4add(o, reinterpret_cast<const float4*>(a.aux + (int64_t)r * a.lda)[c4]);
+    amax_bits = amax4(amax_bits, o);
     reinterpret_cast<float4*>(a.out + (int64_t)r * a.ldo)[c4] = o;
   };
   if (RR > 0) {
@@ -442,6 +450,7 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_fwd_kernel(FusedAr
       }
     }
   }
+  if (a.amax_out != nullptr) amax_publish(amax_bits, a.amax_out);
   cluster.sync();   // no CTA may exit while a peer can still read its exchange buffers
 }
 
@@ -509,9 +518,11 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedAr
   const float4 t1 = cluster_column_sum(acc1, sm, part_b, cluster);
   const float4 s1 = make_float4(t0.x / cnt, t0.y / cnt, t0.z / cnt, t0.w / cnt);
   const float4 s2 = make_float4(t1.x / cnt, t1.y / cnt, t1.z / cnt, t1.w / cnt);
+  unsigned amax_bits = 0u;
   auto finish = [&](const float4& yh, const float4& dz, int r) {
     const float4 o = make_float4(rs.x * (dz.x - s1.x - yh.x * s2.x), rs.y * (dz.y - s1.y - yh.y * s2.y),
                                  rs.z * (dz.z - s1.z - yh.z * s2.z), rs.w * (dz.w - s1.w - yh.w * s2.w));
+    amax_bits = amax4(amax_bits, o);
     reinterpret_cast<float4*>(a.out + (int64_t)r * a.ldo)[c4] = o;
   };
   if (RR > 0) {
@@ -540,6 +551,7 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedAr
       }
     }
   }
+  if (a.amax_out != nullptr) amax_publish(amax_bits, a.amax_out);
   cluster.sync();
 }
 
@@ -664,8 +676,14 @@ extern "C" int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows,
 extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
                                   int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, float eps,
                                   const float* residual, int64_t ldr, int act, float* out, int64_t ldo, float* mean,
-                                  float* rstd, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+                                  float* rstd, float* amax_out, void* workspace, size_t workspace_bytes,
+                                  stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  unsigned* am = reinterpret_cast<unsigned*>(amax_out);
+  if (am != nullptr) {
+    cudaError_t e = cudaMemsetAsync(am, 0, sizeof(unsigned), s);
+    STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "segnorm_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
   STINET_REQUIRE(x && slice_ptr && cnt && mean && rstd && out, STINET_ERR_ARG, "segnorm_fwd: null pointer");
   STINET_REQUIRE(n_rows >= 0 && channels > 0 && n_seg > 0 && n_seg <= 65535 && ldx >= channels && ldo >= channels &&
                      (!residual || ldr >= channels),
@@ -674,7 +692,7 @@ extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, i
   const bool vec = nvec(channels, {x, out, residual, mean, rstd}, {ldx, ldo, residual ? ldr : 0});
   if (vec && max_seg_rows <= kFusedMaxRows) {
     const FusedPlan pl = fused_plan(max_seg_rows);
-    FusedArgs a{x, ldx, residual, ldr, slice_ptr, cnt, mean, rstd, out, ldo, (int)channels, act, eps};
+    FusedArgs a{x, ldx, residual, ldr, slice_ptr, cnt, mean, rstd, out, ldo, (int)channels, act, eps, am};
     return pl.cached ? launch_fused(segnorm_fused_fwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
                      : launch_fused(segnorm_fused_fwd_kernel<0>, a, n_seg, pl.cluster, s);
   }
@@ -686,21 +704,28 @@ extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, i
     const int tyn = kNormThreads / (groups < kTileGroups ? groups : kTileGroups);
     dim3 grid((unsigned)ceil_div(max_seg_rows, tyn * kApplyU * 2), (unsigned)n_seg, (unsigned)ceil_div(groups, kTileGroups));
     K(segnorm_slice_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, residual, ldr, slice_ptr, (int)channels, mean,
-                                                                      rstd, nullptr, nullptr, act, out, ldo));
+                                                                      rstd, nullptr, nullptr, act, out, ldo, am));
     return check_launch("segnorm_fwd");
   }
   // odd widths: the per-row lookup kernel needs a graph id; a single slice uses id 0
   STINET_REQUIRE(n_seg == 1, STINET_ERR_UNSUPPORTED, "segnorm_fwd: channel count %lld (not a multiple of 4) with %lld slices",
                  (long long)channels, (long long)n_seg);
-  return stinet_segnorm_apply(x, ldx, n_rows, channels, nullptr, mean, rstd, residual, ldr, act, out, ldo, stream_);
+  rc = stinet_segnorm_apply(x, ldx, n_rows, channels, nullptr, mean, rstd, residual, ldr, act, out, ldo, stream_);
+  if (rc == STINET_OK && amax_out != nullptr) rc = stinet_f16_amax(out, ldo, n_rows, channels, amax_out, stream_);
+  return rc;
 }
 
 extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows,
                                   int64_t channels, int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr,
                                   const float* cnt, const int32_t* gid, const float* mean, const float* rstd, int act,
-                                  float* dx, int64_t lddx, void* workspace, size_t workspace_bytes,
+                                  float* dx, int64_t lddx, float* amax_out, void* workspace, size_t workspace_bytes,
                                   stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  unsigned* am = reinterpret_cast<unsigned*>(amax_out);
+  if (am != nullptr) {
+    cudaError_t e = cudaMemsetAsync(am, 0, sizeof(unsigned), s);
+    STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "segnorm_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
   STINET_REQUIRE(x && dout && dx && ((mean == nullptr) == (rstd == nullptr)), STINET_ERR_ARG, "segnorm_bwd: null pointer");
   STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldx >= channels && ldg >= channels && lddx >= channels,
                  STINET_ERR_ARG, "segnorm_bwd: bad shape");
@@ -714,7 +739,7 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     STINET_REQUIRE(slice_ptr && cnt && n_seg > 0 && n_seg <= 65535, STINET_ERR_ARG, "segnorm_bwd: segments required");
     const FusedPlan pl = fused_plan(max_seg_rows);
     FusedArgs a{x, ldx, dout, ldg, slice_ptr, cnt, const_cast<float*>(mean), const_cast<float*>(rstd), dx, lddx,
-                (int)channels, act, 0.f};
+                (int)channels, act, 0.f, am};
     return pl.cached ? launch_fused(segnorm_fused_bwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
                      : launch_fused(segnorm_fused_bwd_kernel<0>, a, n_seg, pl.cluster, s);
   }
@@ -736,11 +761,13 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     const int tyn = kNormThreads / (groups < kTileGroups ? groups : kTileGroups);
     dim3 grid2((unsigned)ceil_div(max_seg_rows, tyn * kApplyU * 2), (unsigned)n_seg, (unsigned)ceil_div(groups, kTileGroups));
     K(segnorm_slice_apply_kernel<true><<<grid2, kNormThreads, 0, s>>>(x, ldx, dout, ldg, slice_ptr, (int)channels, mean, rstd,
-                                                                      s1, s2, act, dx, lddx));
+                                                                      s1, s2, act, dx, lddx, am));
     return check_launch("segnorm_bwd");
   }
   const int grid = wave_grid(n_rows * (channels / (vec ? 4 : 1)), kNormThreads * 4, 8, 8);
   if (vec) K(segnorm_bwd_apply_kernel<true><<<grid, kNormThreads, 0, s>>>(x, ldx, dout, ldg, n_rows, (int)channels, gid, mean, rstd, s1, s2, act, dx, lddx));
   else K(segnorm_bwd_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, dout, ldg, n_rows, (int)channels, gid, mean, rstd, s1, s2, act, dx, lddx));
-  return check_launch("segnorm_bwd");
+  int rc = check_launch("segnorm_bwd");
+  if (rc == STINET_OK && amax_out != nullptr) rc = stinet_f16_amax(dx, lddx, n_rows, channels, amax_out, stream_);
+  return rc;
 }

@@ -43,9 +43,9 @@ SIGNATURES = {
     "stinet_unpool_bwd": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_segnorm_workspace_bytes": (SZ, [I64, I64, I64]),
     "stinet_segnorm_stats": (I, [P, I64, I64, I64, I64, I64, P, P, P, F, P, P, P, SZ, P]),
-    "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, SZ, P]),
+    "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, P, SZ, P]),
     "stinet_segnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, I64, P]),
-    "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, SZ, P]),
+    "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, P, SZ, P]),
     "stinet_metrics_workspace_bytes": (SZ, [I64]),
     "stinet_graph_laplace": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_graph_laplace_variance": (I, [P, I64, P, P, I64, P, P, SZ, P]),
@@ -57,10 +57,14 @@ SIGNATURES = {
     "stinet_linear_wgrad": (I, [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I, P, SZ, P]),
     "stinet_f16_amax": (I, [P, I64, I64, I64, P, P]),
     "stinet_f16_split": (I, [P, I64, I64, I64, P, P, P, I64, P, P]),
-    "stinet_linear_fwd_f16": (I, [P, P, I64, P, P, P, I64, P, P, P, P, I64, I64, I64, I64, I, P, SZ, P]),
-    "stinet_linear_dgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, I64, I64, I64, I, P, SZ, P]),
+    "stinet_linear_fwd_f16": (I, [P, P, I64, P, P, P, I64, P, P, P, P, I64, P, I64, I64, I64, I, P, SZ, P]),
+    "stinet_linear_dgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, P, I64, I64, I64, I, P, SZ, P]),
     "stinet_linear_wgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, I64, I64, I64, I, P, SZ, P]),
     "stinet_colsum": (I, [P, I64, P, I64, I64, P, P, SZ, P]),
+    "stinet_colsum_planes": (I, [P, P, I64, P, I64, I64, P, P, SZ, P]),
+    "stinet_csr_dq_factor": (I, [P, P, P, I64, P, P]),
+    "stinet_edge_message_fwd_planes": (I, [P, I64, P, I64, P, P, I64, I64, P, P, P, I64, P, P, P]),
+    "stinet_edge_message_bwd_planes": (I, [P, I64, P, P, P, P, P, P, P, I64, I64, P, P, I64, P, P]),
 }
 
 REDUCE = {"add": 0, "sum": 0, "mean": 1, "max": 2}

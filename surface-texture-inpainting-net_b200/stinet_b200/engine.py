@@ -124,6 +124,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         if self.reducer is not None:
             self.reducer.overlap = False                 # hooks must not launch collectives inside the capture
+        from . import ops
+        ops.invalidate_planes()                          # the graph must contain the split of every operand it reads
         n0 = _abi.query("stinet_launch_count")
         try:
             # with a process group alive, NCCL's watchdog thread polls CUDA events while we capture: only this thread's

@@ -105,6 +105,17 @@ class EdgeCSR:
             self._by_source = (rowptr_s, col_s, eid_s)
         return self._by_source
 
+    def dq_factor(self) -> torch.Tensor:
+        """Device float: max_j sum_{j->i} 1/deg_i -- |dQ| <= max|dhid| * dq_factor in the message-stage backward (the
+        bound its fp16 output planes are scaled with)."""
+        if getattr(self, "_dq_factor", None) is None:
+            rowptr_s, col_s, _ = self.by_source()
+            out = torch.empty(1, dtype=torch.float32, device=self.rowptr_t.device)
+            _abi.call("stinet_csr_dq_factor", self.rowptr_t.data_ptr(), rowptr_s.data_ptr(), col_s.data_ptr(), self.n,
+                      out.data_ptr(), _stream(), cost=(8 * self.e + 8 * self.n, 0, ""))
+            self._dq_factor = out
+        return self._dq_factor
+
     @property
     def degree(self) -> torch.Tensor:
         """int32 in-degree per vertex (rowmask for the `isolated vertex -> 0` rule)."""

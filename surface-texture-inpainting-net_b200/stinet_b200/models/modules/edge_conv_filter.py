@@ -62,10 +62,30 @@ class EdgeConv(torch.nn.Module):
                 m = layer(m)
         return ops.pool_mean(m, by_target)
 
+    def _fused_forward(self, x, csr):
+        """The whole conv as one autograd node on operand planes (ops.EdgeConvFn); input widths that are not a multiple
+        of 4 (the 10-channel first block) are zero-padded -- the extra products are exact zeros."""
+        lin0, lin2 = self.nn[0], self.nn[2]
+        if self.precision not in ("fp32", "f16") or lin0.out_features % 4 or lin2.out_features % 4:
+            return None
+        w0 = lin0.weight
+        pad = (-x.shape[1]) % 4
+        if pad:
+            x = torch.nn.functional.pad(x, (0, pad))
+            if self.trans_inv:
+                w0 = torch.nn.functional.pad(w0, (0, pad))
+            else:
+                h, k2 = w0.shape
+                w0 = torch.nn.functional.pad(w0.view(h, 2, k2 // 2), (0, pad)).reshape(h, -1)
+        return ops.edge_conv(x, w0, lin0.bias, lin2.weight, lin2.bias, csr, self.trans_inv, self.precision)
+
     def forward(self, x, edge_index):
         csr = as_edge_csr(edge_index, x.shape[0])
         if not self.hoistable:
             return self.literal_forward(x, csr)
+        fused = self._fused_forward(x, csr)
+        if fused is not None:
+            return fused
         wcat, bcat = self.hoisted_first_layer()
         pq = ops.linear(x, wcat, bcat, None, self.precision)
         hid = ops.edge_message(pq, csr)

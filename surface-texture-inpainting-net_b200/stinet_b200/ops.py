@@ -47,113 +47,6 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 # dense layers
 
 
-class Planes:
-    """fp16 hi / lo planes of a scaled fp32 matrix and the device scalar exp = -s (include/stinet_b200.h, "operand
-    PLANES").  Produced once per matrix and shared by every dense layer that reads it (fwd + wgrad for activations,
-    dgrad + wgrad for output gradients, fwd + dgrad for weights)."""
-    __slots__ = ("hi", "lo", "exp", "rows", "cols", "ld")
-
-    def __init__(self, hi, lo, exp, rows, cols, ld):
-        self.hi, self.lo, self.exp, self.rows, self.cols, self.ld = hi, lo, exp, rows, cols, ld
-
-
-_plane_epoch = 0
-
-
-def invalidate_planes() -> None:
-    """Forget every cached plane set (called before a CUDA-graph capture: a graph must contain the split kernels of
-    everything it reads, it may not lean on planes computed outside of it)."""
-    global _plane_epoch
-    _plane_epoch += 1
-
-
-def set_amax(t: torch.Tensor, amax: torch.Tensor) -> torch.Tensor:
-    """A producer kernel already knows max|t| (or an upper bound): planes_of(t) then skips its reduction pass."""
-    t._stinet_amax = (t._version, amax)
-    return t
-
-
-def planes_of(t: torch.Tensor, need_lo: bool = True) -> Planes:
-    """The operand planes of fp32 matrix `t`, cached on the tensor object (keyed by its version counter)."""
-    cached = getattr(t, "_stinet_planes", None)
-    if cached is not None and cached[0] == t._version and cached[1] == _plane_epoch and (cached[2].lo is not None or not need_lo):
-        return cached[2]
-    x = _mat(t)
-    rows, cols = x.shape
-    dev = x.device
-    s = _stream()
-    known = getattr(t, "_stinet_amax", None)
-    if known is not None and known[0] == t._version:
-        amax = known[1]
-    else:
-        amax = torch.empty(1, dtype=torch.float32, device=dev)
-        _abi.call("stinet_f16_amax", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), s,
-                  cost=(4 * rows * cols, 0, ""))
-    ld = (cols + 7) & ~7
-    hi = torch.empty((rows, ld), dtype=torch.float16, device=dev)
-    lo = torch.empty((rows, ld), dtype=torch.float16, device=dev) if need_lo else None
-    exp = torch.empty(1, dtype=torch.int32, device=dev)
-    _abi.call("stinet_f16_split", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), hi.data_ptr(), _ptr(lo), ld,
-              exp.data_ptr(), s, cost=(rows * cols * (4 + (4 if need_lo else 2)), 0, ""))
-    p = Planes(hi, lo, exp, rows, cols, ld)
-    t._stinet_planes = (t._version, _plane_epoch, p)
-    return p
-
-
-class LinearPlanesFn(Function):
-    """y = x W^T + b on fp16 operand planes (tcgen05 kind::f16; passes = 3: fp32-class result, 1: 11-bit operands)."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, rowmask, passes):
-        need_lo = passes == 3
-        xp, wp = planes_of(x, need_lo), planes_of(weight, need_lo)
-        M, K = xp.rows, xp.cols
-        N = wp.rows
-        assert wp.cols == K
-        dev = xp.hi.device
-        y = torch.empty((M, N), dtype=torch.float32, device=dev)
-        nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
-        ws = _ws(nb, dev)
-        _abi.call("stinet_linear_fwd_f16", xp.hi.data_ptr(), _ptr(xp.lo), xp.ld, xp.exp.data_ptr(), wp.hi.data_ptr(),
-                  _ptr(wp.lo), wp.ld, wp.exp.data_ptr(), _ptr(bias), _ptr(rowmask), y.data_ptr(), N, M, N, K, passes,
-                  ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
-        ctx.xp, ctx.wp, ctx.rowmask = xp, wp, rowmask
-        ctx.has_bias, ctx.passes = bias is not None, passes
-        return y
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, dy):
-        xp, wp, rowmask, passes = ctx.xp, ctx.wp, ctx.rowmask, ctx.passes
-        M, K, N = xp.rows, xp.cols, wp.rows
-        dev = xp.hi.device
-        dyp = planes_of(dy, passes == 3)
-        nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
-        ws = _ws(nb, dev)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty((M, K), dtype=torch.float32, device=dev)
-            _abi.call("stinet_linear_dgrad_f16", dyp.hi.data_ptr(), _ptr(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
-                      wp.hi.data_ptr(), _ptr(wp.lo), wp.ld, wp.exp.data_ptr(), dx.data_ptr(), K, M, N, K, passes,
-                      ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty((N, K), dtype=torch.float32, device=dev)
-            if M > 0:
-                _abi.call("stinet_linear_wgrad_f16", dyp.hi.data_ptr(), _ptr(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
-                          xp.hi.data_ptr(), _ptr(xp.lo), xp.ld, xp.exp.data_ptr(), dw.data_ptr(), K, M, N, K, passes,
-                          ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
-            else:
-                dw.zero_()
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            dym = _mat(dy)
-            db = torch.empty((N,), dtype=torch.float32, device=dev)
-            nbc = _abi.query("stinet_gemm_workspace_bytes", M, N, 1, 0)
-            wsc = _ws(nbc, dev)
-            _abi.call("stinet_colsum", dym.data_ptr(), _ld(dym), _ptr(rowmask), M, N, db.data_ptr(), wsc.data_ptr(), nbc,
-                      _stream(), cost=(4 * M * N, 0, f"N{N}"))
-        return dx, dw, db, None, None
-
-
 class LinearFn(Function):
     """y = x W^T + b, bias only on rows with rowmask > 0 when a rowmask is given."""
 
@@ -197,6 +90,246 @@ class LinearFn(Function):
                       dw.data_ptr(), K, _ptr(db), M, N, K, ctx.prec, ws.data_ptr(), nb, _stream(),
                       cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
         return dx, dw, db, None, None
+
+
+class Planes:
+    """fp16 hi / lo planes of a scaled fp32 matrix and the device scalar exp = -s (include/stinet_b200.h, "operand
+    PLANES").  Produced once per matrix and shared by every dense layer that reads it (fwd + wgrad for activations,
+    dgrad + wgrad for output gradients, fwd + dgrad for weights)."""
+    __slots__ = ("hi", "lo", "exp", "rows", "cols", "ld")
+
+    def __init__(self, hi, lo, exp, rows, cols, ld):
+        self.hi, self.lo, self.exp, self.rows, self.cols, self.ld = hi, lo, exp, rows, cols, ld
+
+
+_plane_epoch = 0
+
+
+def invalidate_planes() -> None:
+    """Forget every cached plane set (called before a CUDA-graph capture: a graph must contain the split kernels of
+    everything it reads, it may not lean on planes computed outside of it)."""
+    global _plane_epoch
+    _plane_epoch += 1
+
+
+def set_amax(t: torch.Tensor, amax: torch.Tensor) -> torch.Tensor:
+    """A producer kernel already knows max|t| (or an upper bound): planes_of(t) then skips its reduction pass."""
+    t._stinet_amax = (t._version, amax)
+    return t
+
+
+def planes_of(t: torch.Tensor, need_lo: bool = True) -> Planes:
+    """The operand planes of fp32 matrix `t`, cached on the tensor object (keyed by its version counter)."""
+    # Parameters are never cached: fused / foreach optimizers update them without touching the version counter, so a
+    # split taken in one step says nothing about the next one (one split per forward, shared with backward through ctx)
+    cacheable = not (t.is_leaf and t.requires_grad)
+    cached = getattr(t, "_stinet_planes", None) if cacheable else None
+    if cached is not None and cached[0] == t._version and cached[1] == _plane_epoch and (cached[2].lo is not None or not need_lo):
+        return cached[2]
+    x = _mat(t)
+    rows, cols = x.shape
+    dev = x.device
+    s = _stream()
+    known = getattr(t, "_stinet_amax", None)
+    if known is not None and known[0] == t._version:
+        amax = known[1]
+    else:
+        amax = torch.empty(1, dtype=torch.float32, device=dev)
+        _abi.call("stinet_f16_amax", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), s,
+                  cost=(4 * rows * cols, 0, ""))
+    ld = (cols + 7) & ~7
+    hi = torch.empty((rows, ld), dtype=torch.float16, device=dev)
+    lo = torch.empty((rows, ld), dtype=torch.float16, device=dev) if need_lo else None
+    exp = torch.empty(1, dtype=torch.int32, device=dev)
+    _abi.call("stinet_f16_split", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), hi.data_ptr(), _ptr(lo), ld,
+              exp.data_ptr(), s, cost=(rows * cols * (4 + (4 if need_lo else 2)), 0, ""))
+    p = Planes(hi, lo, exp, rows, cols, ld)
+    if cacheable:
+        t._stinet_planes = (t._version, _plane_epoch, p)
+    return p
+
+
+def _new_planes(rows: int, cols: int, need_lo: bool, dev) -> Planes:
+    ld = (cols + 7) & ~7
+    hi = torch.empty((rows, ld), dtype=torch.float16, device=dev)
+    lo = torch.empty((rows, ld), dtype=torch.float16, device=dev) if need_lo else None
+    return Planes(hi, lo, torch.empty(1, dtype=torch.int32, device=dev), rows, cols, ld)
+
+
+def _pl_fwd(xp: Planes, wp: Planes, bias, rowmask, passes: int, want_amax: bool = False):
+    """y = x W^T + b on planes; optionally also max|y| (device scalar) from the GEMM's epilogue."""
+    M, K, N = xp.rows, xp.cols, wp.rows
+    assert wp.cols == K
+    dev = xp.hi.device
+    y = torch.empty((M, N), dtype=torch.float32, device=dev)
+    amax = torch.empty(1, dtype=torch.float32, device=dev) if want_amax else None
+    nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
+    ws = _ws(nb, dev)
+    _abi.call("stinet_linear_fwd_f16", xp.hi.data_ptr(), _ptr(xp.lo), xp.ld, xp.exp.data_ptr(), wp.hi.data_ptr(),
+              _ptr(wp.lo), wp.ld, wp.exp.data_ptr(), _ptr(bias), _ptr(rowmask), y.data_ptr(), N, _ptr(amax), M, N, K,
+              passes, ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+    return y, amax
+
+
+def _pl_dgrad(dyp: Planes, wp: Planes, passes: int, want_amax: bool = False):
+    M, N, K = dyp.rows, wp.rows, wp.cols
+    assert dyp.cols == N
+    dev = dyp.hi.device
+    dx = torch.empty((M, K), dtype=torch.float32, device=dev)
+    amax = torch.empty(1, dtype=torch.float32, device=dev) if want_amax else None
+    nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
+    ws = _ws(nb, dev)
+    _abi.call("stinet_linear_dgrad_f16", dyp.hi.data_ptr(), _ptr(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
+              wp.hi.data_ptr(), _ptr(wp.lo), wp.ld, wp.exp.data_ptr(), dx.data_ptr(), K, _ptr(amax), M, N, K, passes,
+              ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+    return dx, amax
+
+
+def _pl_wgrad(dyp: Planes, xp: Planes, passes: int):
+    M, N, K = dyp.rows, dyp.cols, xp.cols
+    assert xp.rows == M
+    dev = dyp.hi.device
+    dw = torch.empty((N, K), dtype=torch.float32, device=dev)
+    if M == 0:
+        return dw.zero_()
+    nb = _abi.query("stinet_gemm_workspace_bytes", M, N, K, 0)
+    ws = _ws(nb, dev)
+    _abi.call("stinet_linear_wgrad_f16", dyp.hi.data_ptr(), _ptr(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
+              xp.hi.data_ptr(), _ptr(xp.lo), xp.ld, xp.exp.data_ptr(), dw.data_ptr(), K, M, N, K, passes,
+              ws.data_ptr(), nb, _stream(), cost=(4 * (M * K + N * K + M * N), 2 * M * N * K, f"{N}x{K}"))
+    return dw
+
+
+def _colsum(dy: torch.Tensor, rowmask) -> torch.Tensor:
+    """dbias = masked column sums of dy (deterministic two-stage reduction)."""
+    dym = _mat(dy)
+    M, N = dym.shape
+    db = torch.empty((N,), dtype=torch.float32, device=dym.device)
+    nb = _abi.query("stinet_gemm_workspace_bytes", M, N, 1, 0)
+    ws = _ws(nb, dym.device)
+    _abi.call("stinet_colsum", dym.data_ptr(), _ld(dym), _ptr(rowmask), M, N, db.data_ptr(), ws.data_ptr(), nb,
+              _stream(), cost=(4 * M * N, 0, f"N{N}"))
+    return db
+
+
+class LinearPlanesFn(Function):
+    """y = x W^T + b on fp16 operand planes (tcgen05 kind::f16; passes = 3: fp32-class result, 1: 11-bit operands)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, rowmask, passes):
+        need_lo = passes == 3
+        xp, wp = planes_of(x, need_lo), planes_of(weight, need_lo)
+        y, _ = _pl_fwd(xp, wp, bias, rowmask, passes)
+        ctx.xp, ctx.wp, ctx.rowmask = xp, wp, rowmask
+        ctx.has_bias, ctx.passes = bias is not None, passes
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xp, wp, rowmask, passes = ctx.xp, ctx.wp, ctx.rowmask, ctx.passes
+        dyp = planes_of(dy, passes == 3)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = _pl_dgrad(dyp, wp, passes)
+        if ctx.needs_input_grad[1]:
+            dw = _pl_wgrad(dyp, xp, passes)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(dy, rowmask)
+        return dx, dw, db, None, None
+
+
+# observer(pq, csr) called with the [P | Q] matrix of every fused EdgeConv message stage (tests record the ReLU decisions)
+_edge_message_observer = None
+
+
+class EdgeConvFn(Function):
+    """out_i = mean_{j->i} nn([x_i || x_j - x_i])  (trans_inv: nn(x_j - x_i)),  nn = Lin(.,H) ReLU Lin(H,dout), evaluated in
+    the hoisted form as ONE autograd node on operand planes:
+        [P | Q] = x Wcat^T + [b0 ; 0]          tcgen05 GEMM, epilogue leaves max|PQ|
+        hid     = mean relu(P_i + Q_j)          written as fp16 planes (scale from 2 max|PQ|), ReLU decisions saved
+        out     = hid W2^T + b2 [deg > 0]       tcgen05 GEMM
+    Backward: dhid = dy W2 (epilogue leaves max|dhid|), dPQ written as planes by the message-stage backward, then the
+    two wgrads and the dgrad.  hid and dPQ never exist as fp32 matrices; every operand is split exactly once."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2, csr: EdgeCSR, trans_inv: bool, passes: int):
+        need_lo = passes == 3
+        dev = x.device
+        s = _stream()
+        xp = planes_of(x, need_lo)
+        n, din = xp.rows, xp.cols
+        w0m = _mat(w0)
+        h = w0m.shape[0]
+        kin = w0m.shape[1]
+        assert kin == (din if trans_inv else 2 * din) and n == csr.n
+        dout = w2.shape[0]
+        wcat = torch.empty((2 * h, din), dtype=torch.float32, device=dev)
+        bcat = torch.empty((2 * h,), dtype=torch.float32, device=dev) if b0 is not None else None
+        _abi.call("stinet_edgeconv_hoist_fwd", w0m.data_ptr(), _ld(w0m), _ptr(b0), h, din, int(trans_inv), wcat.data_ptr(),
+                  _ptr(bcat), s, cost=(4 * h * (kin + 2 * din), 0, ""))
+        wcp = planes_of(wcat, need_lo)
+        pq, pq_amax = _pl_fwd(xp, wcp, bcat, None, passes, want_amax=True)
+        if _edge_message_observer is not None:
+            _edge_message_observer(pq, csr)
+        train = any(ctx.needs_input_grad[:5])
+        hidp = _new_planes(n, h, need_lo, dev)
+        mask = torch.empty((max(csr.e, 1), h // 4), dtype=torch.uint8, device=dev) if train else None
+        _abi.call("stinet_edge_message_fwd_planes", pq.data_ptr(), 2 * h, pq.data_ptr() + 4 * h, 2 * h,
+                  csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h, pq_amax.data_ptr(), hidp.hi.data_ptr(),
+                  _ptr(hidp.lo), hidp.ld, hidp.exp.data_ptr(), _ptr(mask), s,
+                  cost=(csr.e * (4 * h + 4 + (h // 4 if train else 0)) + n * (8 * h + 4), 2 * csr.e * h, f"H{h}"))
+        w2p = planes_of(w2, need_lo)
+        y, _ = _pl_fwd(hidp, w2p, b2, csr.degree, passes)
+        if train:
+            ctx.saved = (xp, wcp, hidp, w2p, mask, csr)
+        ctx.dims = (n, din, h, kin, dout, trans_inv, passes, b0 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        xp, wcp, hidp, w2p, mask, csr = ctx.saved
+        n, din, h, kin, dout, trans_inv, passes, has_b0, has_b2 = ctx.dims
+        need_lo = passes == 3
+        dev = dy.device
+        s = _stream()
+        dyp = planes_of(dy, need_lo)
+        # second Linear
+        dhid, dhid_amax = _pl_dgrad(dyp, w2p, passes, want_amax=True)
+        dw2 = _pl_wgrad(dyp, hidp, passes) if ctx.needs_input_grad[3] else None
+        db2 = _colsum(dy, csr.degree) if (has_b2 and ctx.needs_input_grad[4]) else None
+        # message stage: dPQ = [dP | dQ] as planes
+        rowptr_s, col_s, _ = csr.by_source()
+        dpqp = _new_planes(n, 2 * h, need_lo, dev)
+        _abi.call("stinet_edge_message_bwd_planes", dhid.data_ptr(), h, dhid_amax.data_ptr(), csr.dq_factor().data_ptr(),
+                  csr.rowptr_t.data_ptr(), rowptr_s.data_ptr(), col_s.data_ptr(), csr.tpos_s().data_ptr(), mask.data_ptr(),
+                  n, h, dpqp.hi.data_ptr(), _ptr(dpqp.lo), dpqp.ld, dpqp.exp.data_ptr(), s,
+                  cost=(csr.e * (4 * h + h // 2 + 12) + n * (16 * h + 8), 2 * csr.e * h, f"H{h}"))
+        # first (hoisted) Linear
+        dx = _pl_dgrad(dpqp, wcp, passes)[0] if ctx.needs_input_grad[0] else None
+        dw0 = db0 = None
+        if ctx.needs_input_grad[1]:
+            dwcat = _pl_wgrad(dpqp, xp, passes)
+            dw0 = torch.empty((h, kin), dtype=torch.float32, device=dev)
+            _abi.call("stinet_edgeconv_hoist_bwd", dwcat.data_ptr(), None, h, din, int(trans_inv), dw0.data_ptr(), kin, None,
+                      s, cost=(4 * h * (kin + 2 * din), 0, ""))
+        if has_b0 and ctx.needs_input_grad[2]:
+            db0 = torch.empty((h,), dtype=torch.float32, device=dev)
+            nb = _abi.query("stinet_gemm_workspace_bytes", n, h, 1, 0)
+            ws = _ws(nb, dev)
+            _abi.call("stinet_colsum_planes", dpqp.hi.data_ptr(), _ptr(dpqp.lo), dpqp.ld, dpqp.exp.data_ptr(), n, h,
+                      db0.data_ptr(), ws.data_ptr(), nb, s, cost=(4 * n * h, 0, f"N{h}"))
+        return dx, dw0, db0, dw2, db2, None, None, None
+
+
+def edge_conv(x, w0, b0, w2, b2, csr, trans_inv: bool, precision: str):
+    """The fused EdgeConv node when the shapes allow the vector kernels (widths multiples of 4), else None."""
+    passes = _abi.PLANE_PASSES.get(precision)
+    h, dout, din = w0.shape[0], w2.shape[0], x.shape[1]
+    if passes is None or h % 4 or dout % 4 or din % 4 or not x.is_cuda:
+        return None
+    return EdgeConvFn.apply(x, w0, b0, w2, b2, csr, trans_inv, passes)
 
 
 def linear(x, weight, bias=None, rowmask=None, precision="fp32"):
@@ -453,16 +586,25 @@ class UnpoolFn(Function):
         return dxc, None
 
 
+def _carry_amax(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """max / mean pooling and row gathers cannot raise max|x|: the source's bound serves the result's operand planes."""
+    known = getattr(src, "_stinet_amax", None)
+    if known is not None and known[0] == src._version:
+        set_amax(dst, known[1])
+    return dst
+
+
 def pool_max(x, cl):
-    return PoolMaxFn.apply(x, cl)
+    out, arg = PoolMaxFn.apply(x, cl)
+    return _carry_amax(x, out), arg
 
 
 def pool_mean(x, cl):
-    return PoolMeanFn.apply(x, cl)
+    return _carry_amax(x, PoolMeanFn.apply(x, cl))
 
 
 def unpool(xc, cl):
-    return UnpoolFn.apply(xc, cl)
+    return _carry_amax(xc, UnpoolFn.apply(xc, cl))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -471,6 +613,7 @@ def unpool(xc, cl):
 
 class NormActResFn(Function):
     """out = residual + act(instance_norm(x; segments))   (use_norm=False: identity norm)."""
+    last_amax = None      # device scalar max|out| of the most recent forward (picked up by norm_act_res)
 
     @staticmethod
     def forward(ctx, x, residual, seg: Optional[Segments], use_norm: bool, act: int, eps: float):
@@ -487,12 +630,15 @@ class NormActResFn(Function):
             rstd = torch.empty((seg.n_seg, c), dtype=torch.float32, device=dev)
             nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
             ws = _ws(nb, dev)
+        amax = None
         if use_norm and seg.consistent and (seg.n_seg == 1 or _vec_ok(c, x, res)):
-            # slices are the graphs: one entry point (a single cluster kernel when the slices are short)
+            # slices are the graphs: one entry point (a single cluster kernel when the slices are short); the kernels also
+            # leave max|out| behind: the next dense layer's operand planes are scaled with it
+            amax = torch.empty(1, dtype=torch.float32, device=dev)
             _abi.call("stinet_segnorm_fwd", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
                       seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), float(eps), _ptr(res),
                       _ld(res) if res is not None else 0, act, out.data_ptr(), c, mean.data_ptr(), rstd.data_ptr(),
-                      ws.data_ptr(), nb, _stream(), cost=(4 * n * c * (3 + nres), 7 * n * c, f"C{c}"))
+                      amax.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(4 * n * c * (3 + nres), 7 * n * c, f"C{c}"))
         else:
             if use_norm:
                 # the reference's linspace slices cut across graphs (ragged batch), or rows of an odd width: sums by
@@ -506,6 +652,7 @@ class NormActResFn(Function):
                       cost=(4 * n * c * (2 + nres), 4 * n * c, f"C{c}"))
         ctx.save_for_backward(x, mean, rstd)
         ctx.seg, ctx.use_norm, ctx.act, ctx.has_res = seg, use_norm, act, residual is not None
+        NormActResFn.last_amax = amax
         return out
 
     @staticmethod
@@ -525,14 +672,16 @@ class NormActResFn(Function):
                     return dx, dres, None, None, None, None
                 nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
                 ws = _ws(nb, x.device)
+                amax = torch.empty(1, dtype=torch.float32, device=x.device)
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, seg.n_seg,
                           seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(),
                           None if (seg.n_seg == 1 or _vec_ok(c, x, dout)) else _ptr(seg.gid),
-                          mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, ws.data_ptr(), nb, _stream(),
-                          cost=(16 * n * c, 10 * n * c, f"C{c}"))
+                          mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, amax.data_ptr(), ws.data_ptr(), nb,
+                          _stream(), cost=(16 * n * c, 10 * n * c, f"C{c}"))
+                set_amax(dx, amax)                       # the conv's backward splits dx into planes next
             else:
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, 1, n, None,
-                          None, None, None, None, ctx.act, dx.data_ptr(), c, None, 0, _stream())
+                          None, None, None, None, ctx.act, dx.data_ptr(), c, None, None, 0, _stream())
         dres = dout if (ctx.has_res and ctx.needs_input_grad[1]) else None
         return dx, dres, None, None, None, None
 
@@ -572,4 +721,8 @@ def _ragged_norm_backward(x, dout, mean, rstd, seg: Segments, act: int):
 
 
 def norm_act_res(x, residual, seg, use_norm=True, act=ACT_ELU, eps=1e-5):
-    return NormActResFn.apply(x, residual, seg, use_norm, act, eps)
+    out = NormActResFn.apply(x, residual, seg, use_norm, act, eps)
+    if NormActResFn.last_amax is not None:
+        set_amax(out, NormActResFn.last_amax)        # max|out| came with the norm kernels: no reduction pass later
+        NormActResFn.last_amax = None
+    return out

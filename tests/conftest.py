@@ -83,8 +83,16 @@ class cuda_decisions:
             self.choices.append(("pool", arg.detach().long().cpu()))
             return out, arg
 
+        def observer(pq, csr):                       # the fused EdgeConv node (ops.EdgeConvFn) reports its [P | Q] here
+            h = pq.shape[1] // 2
+            with torch.no_grad():
+                m = (pq[csr._dst, :h] + pq[csr._src, h:]) > 0
+            self.choices.append(("relu", m.cpu()))
+
         ops.edge_message, ops.pool_max = edge_message, pool_max
+        ops._edge_message_observer = observer
         return self
 
     def __exit__(self, *exc):
         self.ops.edge_message, self.ops.pool_max = self._em, self._pm
+        self.ops._edge_message_observer = None
