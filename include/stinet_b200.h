@@ -234,6 +234,12 @@ int stinet_linear_wgrad(const float* dC, int64_t ldc, const float* A, int64_t ld
 int stinet_f16_amax(const float* x, int64_t ldx, int64_t rows, int64_t cols, float* amax, stinet_stream_t stream);
 int stinet_f16_split(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* amax, void* hi, void* lo,
                      int64_t ldp, int32_t* exp_out, stinet_stream_t stream);
+/* stinet_f16_split and stinet_colsum in ONE pass over x (the backward of a Linear with bias reads dC for both): planes as
+ * f16_split, colsum[n] = sum_m x[m,n] * (rowmask ? rowmask[m] > 0 : 1).  cols % 8 == 0, 16-byte aligned rows.
+ * workspace: stinet_gemm_workspace_bytes(rows, cols, 1, STINET_PREC_FP32). */
+int stinet_f16_split_colsum(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* amax,
+                            const int32_t* rowmask, void* hi, void* lo, int64_t ldp, int32_t* exp_out, float* colsum,
+                            void* workspace, size_t workspace_bytes, stinet_stream_t stream);
 /* workspace for the three calls below: stinet_gemm_workspace_bytes(M, N, K, STINET_PREC_FP32).
  * amax_out (nullable, float[1]): the GEMM's epilogue also leaves max|C| (C, dA after bias) there, so that the consumer of
  * the result can pick its plane scale without another pass over it. */
@@ -272,7 +278,11 @@ int stinet_edge_message_fwd_planes(const float* P, int64_t ldp, const float* Q, 
 int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* dhid_amax, const float* dq_factor,
                                    const int32_t* rowptr_t, const int32_t* rowptr_s, const int32_t* col_s,
                                    const int32_t* tpos_s, const void* mask, int64_t n_rows, int64_t hidden, void* dpq_hi,
-                                   void* dpq_lo, int64_t ldp, int32_t* dpq_exp, stinet_stream_t stream);
+                                   void* dpq_lo, int64_t ldp, int32_t* dpq_exp, float* dp_colsum, void* workspace,
+                                   size_t workspace_bytes, stinet_stream_t stream);
+/* dp_colsum (nullable, float[hidden]): also sum_i dP[i,:], the bias gradient of the hoisted first Linear, accumulated by the
+ * kernel that produces dP (per-CTA partials in `workspace`, fixed-order second stage). */
+size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden);
 
 /* ---- per-step graph metrics (replace utils/metrics/graph_metrics.py:6-72 as called from
  * trainers/inpainting3d_trainer.py:254-263) on the level-0 CSR by target.  Scalar results are written to `out` on the

@@ -451,12 +451,18 @@ __device__ __forceinline__ int dpq_shift(const unsigned* dhid_amax, const float*
   return plane_shift(__float_as_uint(__uint_as_float(__ldg(dhid_amax)) * fmaxf(1.f, __ldg(dq_factor))));
 }
 
+// COLSUM: the CTA also leaves the column sums of the dP rows it produced in colpart[blockIdx.x][hidden] (the bias gradient
+// of the hoisted first Linear is sum_i dP_i; a second stage adds the CTA partials in fixed order).  Needs
+// (gridDim.x * 8) % nchunk == 0, so that a warp keeps one 128-channel chunk for its whole row loop.
+template <bool COLSUM>
 __global__ void __launch_bounds__(kAggThreads)
 edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr,
                                       const uint8_t* __restrict__ mask, int64_t n_rows, int hidden,
                                       const unsigned* __restrict__ dhid_amax, const float* __restrict__ dq_factor,
                                       __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
-                                      int32_t* __restrict__ exp_out) {
+                                      int32_t* __restrict__ exp_out, float* __restrict__ colpart) {
+  __shared__ float4 csm[COLSUM ? kWarpsPerCta : 1][32];
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
   const int sft = dpq_shift(dhid_amax, dq_factor);
   const float scale = plane_scale(sft);
   if (blockIdx.x == 0 && threadIdx.x == 0) *exp_out = -sft;
@@ -484,6 +490,20 @@ edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ld
       acc.w += (m & 8u) ? d.w : 0.f;
     }
     split_store4(acc, scale, hi + i * ldp + 4 * c4, lo != nullptr ? lo + i * ldp + 4 * c4 : nullptr);
+    if (COLSUM) csum = f4_add(csum, acc);
+  }
+  if (COLSUM) {
+    const int w = threadIdx.x >> 5;
+    csm[w][lane] = csum;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < c4n; idx += kAggThreads) {
+      const int chunk = idx >> 5, l = idx & 31;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ww = 0; ww < kWarpsPerCta; ++ww)      // warps of this CTA that work on `chunk`, in warp order
+        if ((int)(((int64_t)blockIdx.x * kWarpsPerCta + ww) % nchunk) == chunk) t = f4_add(t, csm[ww][l]);
+      reinterpret_cast<float4*>(colpart + (int64_t)blockIdx.x * hidden)[idx] = t;
+    }
   }
 }
 
@@ -734,6 +754,34 @@ extern "C" int stinet_csr_dq_factor(const int32_t* rowptr_t, const int32_t* rowp
   return check_launch("csr_dq_factor");
 }
 
+static size_t edge_bwd_colsum_bytes(int64_t n_rows, int64_t hidden) {
+  int gc = wave_grid((n_rows > 0 ? n_rows : 1) * ceil_div(hidden >> 2, 32), kWarpsPerCta, 8, 1);
+  gc += gc & 1;
+  return sizeof(float) * (size_t)gc * (size_t)hidden;
+}
+extern "C" size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden) {
+  if (n_rows < 0 || hidden <= 0) return 0;
+  return edge_bwd_colsum_bytes(n_rows, hidden);
+}
+
+// out[n] = sum over the rows of part[rows][N], 32 column lanes x 32 row lanes, fixed-order tree over the lanes
+__global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restrict__ part, int rows, int N, float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float t = 0.f;
+  if (n < N)
+    for (int c = ty; c < rows; c += 32) t += part[(int64_t)c * N + n];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float r = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) r += sm[y][tx];
+    out[n] = r;
+  }
+}
+
 static bool planes_ok(int64_t hidden, const void* hi, const void* lo, int64_t ld) {
   return !(hidden & 3) && !(ld & 7) && ld >= hidden && aligned16(hi) && (lo == nullptr || aligned16(lo));
 }
@@ -762,7 +810,8 @@ extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, co
                                               const float* dq_factor, const int32_t* rowptr_t,
                                               const int32_t* rowptr_s, const int32_t* col_s, const int32_t* tpos_s,
                                               const void* mask, int64_t n_rows, int64_t hidden, void* dpq_hi,
-                                              void* dpq_lo, int64_t ldp, int32_t* dpq_exp, stinet_stream_t stream_) {
+                                              void* dpq_lo, int64_t ldp, int32_t* dpq_exp, float* dp_colsum,
+                                              void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   STINET_REQUIRE(dhid && dhid_amax && dq_factor && rowptr_t && rowptr_s && tpos_s && mask && dpq_hi && dpq_exp, STINET_ERR_ARG,
                  "edge_message_bwd_planes: null pointer");
@@ -773,8 +822,22 @@ extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, co
   const unsigned* am = reinterpret_cast<const unsigned*>(dhid_amax);
   __half* hi = static_cast<__half*>(dpq_hi);
   __half* lo = static_cast<__half*>(dpq_lo);
-  K(edge_message_bwd_target_planes_kernel<<<g, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask), n_rows,
-                                                                   (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp));
+  if (dp_colsum != nullptr) {
+    // dbias of the hoisted first Linear = column sums of dP: per-CTA partials from the target kernel, then one fixed-order
+    // reduction.  One wave of CTAs (full occupancy; a partial row per CTA), an even count (see the kernel's chunk rule).
+    int gc = wave_grid(n_rows * ceil_div(hidden >> 2, 32), kWarpsPerCta, 8, 1);
+    gc += gc & 1;
+    const size_t need = edge_bwd_colsum_bytes(n_rows, hidden);
+    STINET_REQUIRE(workspace && workspace_bytes >= need, STINET_ERR_WORKSPACE, "edge_message_bwd_planes: workspace %zu < %zu",
+                   workspace_bytes, need);
+    float* part = static_cast<float*>(workspace);
+    K(edge_message_bwd_target_planes_kernel<true><<<gc, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
+                                                                            n_rows, (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp, part));
+    K(colsum_rows_kernel<<<(unsigned)ceil_div(hidden, 32), 1024, 0, s>>>(part, gc, (int)hidden, dp_colsum));
+  } else {
+    K(edge_message_bwd_target_planes_kernel<false><<<g, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
+                                                                            n_rows, (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp, nullptr));
+  }
   if (n_rows > 0)
     K(edge_message_bwd_source_planes_kernel<<<g, kAggThreads, 0, s>>>(
         dhid, ldd, rowptr_t, rowptr_s, col_s, tpos_s, static_cast<const uint8_t*>(mask), n_rows, (int)hidden, am, dq_factor,

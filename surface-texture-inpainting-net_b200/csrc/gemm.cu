@@ -462,6 +462,64 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
   }
 }
 
+// split + masked column sums in one pass over dC (the backward of a Linear with bias needs both: the planes for dgrad /
+// wgrad and dbias): CTA = CL column lanes (8 columns each) x 256/CL row lanes over one row chunk; stage-1 partials as in
+// colsum_partial_vec_kernel (same chunking, same second stage), so dbias keeps its fixed summation order.
+template <int CL>
+__global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restrict__ x, int64_t ldx, int64_t M, int N,
+                                                           const unsigned* __restrict__ amax, const int32_t* __restrict__ rowmask,
+                                                           int rows_per_chunk, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                           int64_t ldp, int32_t* __restrict__ exp_out, float* __restrict__ part) {
+  constexpr int RL = 256 / CL;
+  __shared__ float4 sm[2][RL][CL];
+  const int sft = plane_shift(__ldg(amax));
+  const float scale = plane_scale(sft);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *exp_out = -sft;
+  const int tx = threadIdx.x % CL, ty = threadIdx.x / CL;
+  const int n0 = (blockIdx.x * CL + tx) * 8;
+  const int64_t m0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t m1 = min(M, m0 + rows_per_chunk);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  if (n0 < N) {
+    for (int64_t m = m0 + ty; m < m1; m += 2 * RL) {
+      float4 v[2][2];
+      bool on[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t mm = m + u * RL;
+        on[u] = false;
+        v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mm < m1) {
+          v[u][0] = ld_stream(reinterpret_cast<const float4*>(x + mm * ldx + n0));
+          v[u][1] = ld_stream(reinterpret_cast<const float4*>(x + mm * ldx + n0 + 4));
+          on[u] = rowmask == nullptr || rowmask[mm] > 0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t mm = m + u * RL;
+        if (mm < m1) {
+          split_store4(v[u][0], scale, hi + mm * ldp + n0, lo != nullptr ? lo + mm * ldp + n0 : nullptr);
+          split_store4(v[u][1], scale, hi + mm * ldp + n0 + 4, lo != nullptr ? lo + mm * ldp + n0 + 4 : nullptr);
+          if (on[u]) {
+            a0.x += v[u][0].x; a0.y += v[u][0].y; a0.z += v[u][0].z; a0.w += v[u][0].w;
+            a1.x += v[u][1].x; a1.y += v[u][1].y; a1.z += v[u][1].z; a1.w += v[u][1].w;
+          }
+        }
+      }
+    }
+  }
+  sm[0][ty][tx] = a0;
+  sm[1][ty][tx] = a1;
+  __syncthreads();
+  if (ty < 2 && n0 < N) {          // row lane 0 sums the first four columns of the group, row lane 1 the other four
+    float4 t = sm[ty][0][tx];
+#pragma unroll
+    for (int y = 1; y < RL; ++y) { const float4 q = sm[ty][y][tx]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+    *reinterpret_cast<float4*>(part + (int64_t)blockIdx.y * N + n0 + 4 * ty) = t;
+  }
+}
+
 // fp32 -> bf16 cast of a row-major matrix (bf16 mode: the tensor-core kernel reads bf16 operands through TMA).
 // cols % 8 == 0, 16 B aligned rows on both sides; one thread converts 8 elements.
 // With a `lo` plane (bf16x3 mode) the rounding residual x - float(hi) is stored too, so hi + lo carries 16 significand bits.
@@ -947,4 +1005,31 @@ extern "C" int stinet_colsum_planes(const void* hi, const void* lo, int64_t ldp,
                                                    rpc, w.colsum));
   K(colsum_planes_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(w.colsum, chunks, (int)N, exp, out));
   return check_launch("colsum_planes");
+}
+
+extern "C" int stinet_f16_split_colsum(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* amax,
+                                       const int32_t* rowmask, void* hi, void* lo, int64_t ldp, int32_t* exp_out,
+                                       float* colsum, void* workspace, size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && amax && hi && exp_out && colsum, STINET_ERR_ARG, "f16_split_colsum: null pointer");
+  STINET_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ldx >= cols && ldx % 4 == 0 && ldp >= cols && ldp % 8 == 0 &&
+                     cols < (1ll << 31) && aligned16(x) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
+                 STINET_ERR_UNSUPPORTED, "f16_split_colsum: needs cols %% 8 == 0 and 16-byte aligned rows");
+  GemmWs w = carve_gemm(workspace, rows, cols, 1, STINET_PREC_FP32);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "f16_split_colsum: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  const int rpc = colsum_rows(rows, cols);
+  const int chunks = (int)ceil_div(rows, rpc);
+  const unsigned* am = reinterpret_cast<const unsigned*>(amax);
+  if (cols > 128) {
+    dim3 g2((unsigned)ceil_div(cols, 256), (unsigned)chunks);
+    K(split_colsum_kernel<32><<<g2, 256, 0, s>>>(x, ldx, rows, (int)cols, am, rowmask, rpc, static_cast<__half*>(hi),
+                                                 static_cast<__half*>(lo), ldp, exp_out, w.colsum));
+  } else {
+    dim3 g2((unsigned)ceil_div(cols, 64), (unsigned)chunks);
+    K(split_colsum_kernel<8><<<g2, 256, 0, s>>>(x, ldx, rows, (int)cols, am, rowmask, rpc, static_cast<__half*>(hi),
+                                                static_cast<__half*>(lo), ldp, exp_out, w.colsum));
+  }
+  K(colsum_final_kernel<<<(unsigned)ceil_div(cols, 32), 1024, 0, s>>>(w.colsum, chunks, (int)cols, colsum));
+  return check_launch("f16_split_colsum");
 }

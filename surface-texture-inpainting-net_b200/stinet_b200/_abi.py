@@ -61,10 +61,12 @@ SIGNATURES = {
     "stinet_linear_dgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, P, I64, I64, I64, I, P, SZ, P]),
     "stinet_linear_wgrad_f16": (I, [P, P, I64, P, P, P, I64, P, P, I64, I64, I64, I64, I, P, SZ, P]),
     "stinet_colsum": (I, [P, I64, P, I64, I64, P, P, SZ, P]),
+    "stinet_f16_split_colsum": (I, [P, I64, I64, I64, P, P, P, P, I64, P, P, P, SZ, P]),
     "stinet_colsum_planes": (I, [P, P, I64, P, I64, I64, P, P, SZ, P]),
     "stinet_csr_dq_factor": (I, [P, P, P, I64, P, P]),
     "stinet_edge_message_fwd_planes": (I, [P, I64, P, I64, P, P, I64, I64, P, P, P, I64, P, P, P]),
-    "stinet_edge_message_bwd_planes": (I, [P, I64, P, P, P, P, P, P, P, I64, I64, P, P, I64, P, P]),
+    "stinet_edge_message_bwd_planes": (I, [P, I64, P, P, P, P, P, P, P, I64, I64, P, P, I64, P, P, P, SZ, P]),
+    "stinet_edge_message_bwd_workspace_bytes": (SZ, [I64, I64]),
 }
 
 REDUCE = {"add": 0, "sum": 0, "mean": 1, "max": 2}

@@ -7,6 +7,7 @@ current stream.  fp32 storage everywhere; `precision` selects the arithmetic of 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -212,12 +213,49 @@ def _colsum(dy: torch.Tensor, rowmask) -> torch.Tensor:
     return db
 
 
+def planes_and_colsum(t: torch.Tensor, rowmask, need_lo: bool = True):
+    """(operand planes of t, masked column sums of t) -- what the backward of a Linear with bias needs from dC -- in one
+    pass over t when the layout allows the fused kernel, else as two."""
+    x = _mat(t)
+    rows, cols = x.shape
+    cached = getattr(t, "_stinet_planes", None)
+    fused = (cached is None and rows > 0 and cols % 8 == 0 and _ld(x) % 4 == 0 and x.data_ptr() % 16 == 0
+             and not (t.is_leaf and t.requires_grad))
+    if not fused:
+        return planes_of(t, need_lo), _colsum(t, rowmask)
+    dev = x.device
+    s = _stream()
+    known = getattr(t, "_stinet_amax", None)
+    if known is not None and known[0] == t._version:
+        amax = known[1]
+    else:
+        amax = torch.empty(1, dtype=torch.float32, device=dev)
+        _abi.call("stinet_f16_amax", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), s, cost=(4 * rows * cols, 0, ""))
+    p = _new_planes(rows, cols, need_lo, dev)
+    db = torch.empty((cols,), dtype=torch.float32, device=dev)
+    nb = _abi.query("stinet_gemm_workspace_bytes", rows, cols, 1, 0)
+    ws = _ws(nb, dev)
+    _abi.call("stinet_f16_split_colsum", x.data_ptr(), _ld(x), rows, cols, amax.data_ptr(), _ptr(rowmask), p.hi.data_ptr(),
+              _ptr(p.lo), p.ld, p.exp.data_ptr(), db.data_ptr(), ws.data_ptr(), nb, s,
+              cost=(rows * cols * (4 + (4 if need_lo else 2)), 0, ""))
+    t._stinet_planes = (t._version, _plane_epoch, p)
+    return p, db
+
+
+# experiment knob (scripts/diag_f16.py): tcgen05 passes of the BACKWARD GEMMs when the forward runs one pass
+_BWD_PASSES = int(os.environ.get("STINET_F16_BWD_PASSES", "0"))
+
+
+def _bwd_passes(passes: int) -> int:
+    return _BWD_PASSES if (_BWD_PASSES and passes == 1) else passes
+
+
 class LinearPlanesFn(Function):
     """y = x W^T + b on fp16 operand planes (tcgen05 kind::f16; passes = 3: fp32-class result, 1: 11-bit operands)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, rowmask, passes):
-        need_lo = passes == 3
+        need_lo = _bwd_passes(passes) == 3
         xp, wp = planes_of(x, need_lo), planes_of(weight, need_lo)
         y, _ = _pl_fwd(xp, wp, bias, rowmask, passes)
         ctx.xp, ctx.wp, ctx.rowmask = xp, wp, rowmask
@@ -227,15 +265,16 @@ class LinearPlanesFn(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        xp, wp, rowmask, passes = ctx.xp, ctx.wp, ctx.rowmask, ctx.passes
-        dyp = planes_of(dy, passes == 3)
+        xp, wp, rowmask, passes = ctx.xp, ctx.wp, ctx.rowmask, _bwd_passes(ctx.passes)
         dx = dw = db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dyp, db = planes_and_colsum(dy, rowmask, passes == 3)
+        else:
+            dyp = planes_of(dy, passes == 3)
         if ctx.needs_input_grad[0]:
             dx, _ = _pl_dgrad(dyp, wp, passes)
         if ctx.needs_input_grad[1]:
             dw = _pl_wgrad(dyp, xp, passes)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _colsum(dy, rowmask)
         return dx, dw, db, None, None
 
 
@@ -254,7 +293,7 @@ class EdgeConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, w0, b0, w2, b2, csr: EdgeCSR, trans_inv: bool, passes: int):
-        need_lo = passes == 3
+        need_lo = _bwd_passes(passes) == 3
         dev = x.device
         s = _stream()
         xp = planes_of(x, need_lo)
@@ -291,35 +330,37 @@ class EdgeConvFn(Function):
     def backward(ctx, dy):
         xp, wcp, hidp, w2p, mask, csr = ctx.saved
         n, din, h, kin, dout, trans_inv, passes, has_b0, has_b2 = ctx.dims
+        passes = _bwd_passes(passes)
         need_lo = passes == 3
         dev = dy.device
         s = _stream()
-        dyp = planes_of(dy, need_lo)
+        db2 = None
+        if has_b2 and ctx.needs_input_grad[4]:
+            dyp, db2 = planes_and_colsum(dy, csr.degree, need_lo)
+        else:
+            dyp = planes_of(dy, need_lo)
         # second Linear
         dhid, dhid_amax = _pl_dgrad(dyp, w2p, passes, want_amax=True)
         dw2 = _pl_wgrad(dyp, hidp, passes) if ctx.needs_input_grad[3] else None
-        db2 = _colsum(dy, csr.degree) if (has_b2 and ctx.needs_input_grad[4]) else None
         # message stage: dPQ = [dP | dQ] as planes
         rowptr_s, col_s, _ = csr.by_source()
         dpqp = _new_planes(n, 2 * h, need_lo, dev)
+        want_db0 = has_b0 and ctx.needs_input_grad[2]
+        db0 = torch.empty((h,), dtype=torch.float32, device=dev) if want_db0 else None     # = sum_i dP_i, from the same kernel
+        nbe = _abi.query("stinet_edge_message_bwd_workspace_bytes", n, h) if want_db0 else 0
+        wse = _ws(nbe, dev) if want_db0 else None
         _abi.call("stinet_edge_message_bwd_planes", dhid.data_ptr(), h, dhid_amax.data_ptr(), csr.dq_factor().data_ptr(),
                   csr.rowptr_t.data_ptr(), rowptr_s.data_ptr(), col_s.data_ptr(), csr.tpos_s().data_ptr(), mask.data_ptr(),
-                  n, h, dpqp.hi.data_ptr(), _ptr(dpqp.lo), dpqp.ld, dpqp.exp.data_ptr(), s,
+                  n, h, dpqp.hi.data_ptr(), _ptr(dpqp.lo), dpqp.ld, dpqp.exp.data_ptr(), _ptr(db0), _ptr(wse), nbe, s,
                   cost=(csr.e * (4 * h + h // 2 + 12) + n * (16 * h + 8), 2 * csr.e * h, f"H{h}"))
         # first (hoisted) Linear
         dx = _pl_dgrad(dpqp, wcp, passes)[0] if ctx.needs_input_grad[0] else None
-        dw0 = db0 = None
+        dw0 = None
         if ctx.needs_input_grad[1]:
             dwcat = _pl_wgrad(dpqp, xp, passes)
             dw0 = torch.empty((h, kin), dtype=torch.float32, device=dev)
             _abi.call("stinet_edgeconv_hoist_bwd", dwcat.data_ptr(), None, h, din, int(trans_inv), dw0.data_ptr(), kin, None,
                       s, cost=(4 * h * (kin + 2 * din), 0, ""))
-        if has_b0 and ctx.needs_input_grad[2]:
-            db0 = torch.empty((h,), dtype=torch.float32, device=dev)
-            nb = _abi.query("stinet_gemm_workspace_bytes", n, h, 1, 0)
-            ws = _ws(nb, dev)
-            _abi.call("stinet_colsum_planes", dpqp.hi.data_ptr(), _ptr(dpqp.lo), dpqp.ld, dpqp.exp.data_ptr(), n, h,
-                      db0.data_ptr(), ws.data_ptr(), nb, s, cost=(4 * n * h, 0, f"N{h}"))
         return dx, dw0, db0, dw2, db2, None, None, None
 
 
