@@ -81,6 +81,8 @@ WORKLOADS = {
                           n_levels=2, pooling_type="max"),
                  name="tiny debug workload"),
 }
+# tcgen05 passes per algorithmic product and the tensor-pipe rate of the operand type relative to bf16 / fp16
+MODE_COST = {"fp32": (3, 1.0), "f16": (1, 1.0), "bf16x3": (3, 1.0), "bf16": (1, 1.0), "tf32": (1, 0.5), "fp32_tf32x3": (3, 0.5)}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -172,64 +174,18 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 
 
-def run_reference(args, wl, rank, world):
-    """--impl reference: the reference's algorithm for the path on the host cores.  torch_geometric / torch_scatter
-    cannot be installed in this image, so this is the CPU oracle port (kind='port'); each step is a bounded sample of
-    the workload: ONE graph of the batch, forward + loss + backward (recompute off)."""
-    if rank != 0:
-        return
+REFERENCE_BUDGET_S = 300.0      # wall-clock bound of one --impl reference run (the driver calls it at every N)
+
+
+def _oracle_job(wl, n_graphs):
+    """(net, batch, step) of the CPU oracle port on `n_graphs` graphs of the workload: fwd + masked-L1 + bwd (recompute
+    off), or the forward alone for the inference workload."""
     from oracle import stinet_oracle as O
     from stinet_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(49)
     nk = {("norm_type" if k == "norm" else k): v for k, v in wl["net"].items()}
     net = O.OracleSTINet(**nk)
-    b = synthetic.make_batch(wl["kind"], 1, wl["net"]["n_levels"], seed=49, **wl["gen"])
-    n0 = b.x.shape[0]
-    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-
-    infer = wl.get("mode") == "infer"
-
-    def step():
-        if infer:
-            with torch.no_grad():
-                net(b)
-            return
-        net.zero_grad(set_to_none=True)
-        out = net(b)
-        O.masked_l1_loss(out, b).backward()
-
-    for _ in range(warm):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    v = n0 / dt
-    what = "forward (eval, no_grad)" if infer else "fwd+loss+bwd"
-    sample = f"1 of {wl['batch']} graphs ({n0} vertices), {what}, {steps} timed steps after {warm} warm-up"
-    emit({
-        "impl": "reference", "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": v, "unit": "vertices/s", "n_gpus": 0,
-        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "vertices/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    })
-
-
-def cpu_baseline(wl, budget_s=25.0):
-    from oracle import stinet_oracle as O
-    from stinet_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(49)
-    nk = {("norm_type" if k == "norm" else k): v for k, v in wl["net"].items()}
-    net = O.OracleSTINet(**nk)
-    b = synthetic.make_batch(wl["kind"], 1, wl["net"]["n_levels"], seed=49, **wl["gen"])
-
+    b = synthetic.make_batch(wl["kind"], n_graphs, wl["net"]["n_levels"], seed=49, **wl["gen"])
     infer = wl.get("mode") == "infer"
 
     def step():
@@ -240,16 +196,75 @@ def cpu_baseline(wl, budget_s=25.0):
         net.zero_grad(set_to_none=True)
         O.masked_l1_loss(net(b), b).backward()
 
+    return net, b, step
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's algorithm for the path on the host cores, all threads.  torch_geometric /
+    torch_scatter cannot be installed in this image, so this is the CPU oracle port (kind='port').  A step is the WHOLE
+    batch of the workload (same config as the stinet arm: per-graph norms, B graphs); --steps / --warmup are honoured and
+    only cut short if the run would exceed REFERENCE_BUDGET_S (then the line says how many steps were timed)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    infer = wl.get("mode") == "infer"
+    _, b, step = _oracle_job(wl, wl["batch"])
+    n0 = b.x.shape[0]
+    t_begin = time.perf_counter()
+    step()                                                   # first warm-up step, also calibrates the budget
+    t_one = time.perf_counter() - t_begin
+    warm = max(1, args.warmup)
+    steps = max(1, args.steps)
+    fit = int(REFERENCE_BUDGET_S / max(t_one, 1e-3))         # steps (warm-up included) that fit the budget
+    if warm + steps > fit:
+        warm = max(1, min(warm, fit // 4))
+        steps = max(1, fit - warm)
+    for _ in range(warm - 1):
+        step()
     t0 = time.perf_counter()
-    step()                                       # warm-up, also calibrates the budget
-    warm = time.perf_counter() - t0
-    n = max(1, min(5, int(budget_s / max(warm, 1e-3)) - 1))
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    v = n0 / dt
+    what = "forward (eval, no_grad)" if infer else "fwd+loss+bwd"
+    sample = (f"whole batch: {wl['batch']} graph(s), {n0} vertices, {what}, {steps} timed steps after {warm} warm-up"
+              + ("" if (steps == max(1, args.steps) and warm == max(1, args.warmup)) else
+                 f" (asked for {args.steps}/{args.warmup}; cut to fit {REFERENCE_BUDGET_S:.0f} s)"))
+    emit({
+        "impl": "reference", "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": v, "unit": "vertices/s", "n_gpus": 0,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "vertices_per_step_per_gpu": n0, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "vertices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+
+
+def cpu_baseline(wl, budget_s=25.0):
+    """The same CPU oracle port on a bounded sample for the stinet arm's JSON line: the whole batch when one step of it
+    fits the budget twice, else one graph."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    infer = wl.get("mode") == "infer"
+    _, b1, step1 = _oracle_job(wl, 1)
+    t0 = time.perf_counter()
+    step1()                                      # warm-up on ONE graph, also calibrates the budget
+    t_graph = time.perf_counter() - t0
+    n_graphs = wl["batch"] if 3 * t_graph * wl["batch"] <= budget_s else 1
+    if n_graphs == 1:
+        b, step = b1, step1
+    else:
+        _, b, step = _oracle_job(wl, n_graphs)
+        step()
+    n = max(1, min(5, int(budget_s / max(t_graph * n_graphs, 1e-3)) - 1))
     t0 = time.perf_counter()
     for _ in range(n):
         step()
     dt = (time.perf_counter() - t0) / n
     return {"value": b.x.shape[0] / dt, "unit": "vertices/s", "cores": cores, "kind": "port",
-            "sample": f"CPU oracle port (PyG absent), 1 of {wl['batch']} graphs ({b.x.shape[0]} vertices), "
+            "sample": f"CPU oracle port (PyG absent), {n_graphs} of {wl['batch']} graphs ({b.x.shape[0]} vertices), "
                       f"{'forward (eval, no_grad)' if infer else 'fwd+loss+bwd'}, "
                       f"{n} timed steps after 1 warm-up, fp32, recompute off"}
 
@@ -261,9 +276,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="stinet", choices=["stinet", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16", "bf16_1pass", "tf32"],
-                    help="arithmetic of the dense layers: fp32 = 3xTF32 tcgen05 (1e-5 parity); bf16 = bf16 tcgen05 tiles on "
-                         "hi/lo-split operands (whole network within 2e-2); bf16_1pass = one bf16 pass (2e-2 per operator)")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "f16", "bf16", "bf16x3", "bf16_1pass", "tf32", "tf32x3"],
+                    help="arithmetic of the dense layers (tcgen05, fp32 accumulate): fp32 = three kind::f16 passes on scaled fp16 "
+                         "hi/lo operand planes (fp32-class, the 1e-5 parity mode); f16 (alias bf16: the 16-bit mode BASELINE's "
+                         "config 5 asks for) = ONE kind::f16 pass on the hi planes (11-bit operands: outputs within 2e-2); "
+                         "bf16x3 / bf16_1pass = bf16 tiles (3 passes / 1 pass); tf32x3 = round 1's 3xTF32 mode; tf32 = one pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (used under ncu only)")
@@ -294,7 +311,8 @@ def main():
     W, K = max(args.warmup, 3), args.steps
 
     torch.manual_seed(49)                                    # same initial weights on every rank
-    precision = {"fp32": "fp32", "bf16": "bf16x3", "bf16_1pass": "bf16", "tf32": "tf32"}[args.dtype]
+    precision = {"fp32": "fp32", "f16": "f16", "bf16": "f16", "bf16x3": "bf16x3", "bf16_1pass": "bf16", "tf32": "tf32",
+                 "tf32x3": "fp32_tf32x3"}[args.dtype]
     infer = wl.get("mode") == "infer"
     net = S.define_G(**wl["net"], gpu_ids=[dev], precision=precision)
     net = net.eval() if infer else net.train()
@@ -465,9 +483,11 @@ def main():
                         "TFLOPs": r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else None}
                     for k, r in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}}, f, indent=1)
         # dominant kernel = the kernel FAMILY (entry point, all shapes) with the largest share of device time
+        # (the three dense-layer entry points fwd / dgrad / wgrad run ONE kernel, gemm_tc_kernel: one family)
         fam = {}
         for k, r in summ.items():
-            f = fam.setdefault(k.split("[")[0], {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            name = k.split("[")[0]
+            f = fam.setdefault("linear" if name.startswith("linear") else name, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
             for q in f:
                 f[q] += r[q]
         top, r = max(fam.items(), key=lambda kv: kv[1]["ms"])
@@ -475,8 +495,8 @@ def main():
         if top.startswith("linear"):
             ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
             # MMA passes per algorithmic product, and the tensor-pipe rate of the operand type relative to bf16
-            passes, rate = {"fp32": (3, 0.5), "bf16x3": (3, 1.0), "bf16": (1, 1.0), "tf32": (1, 0.5)}[precision]
-            roofline = {"kernel": f"gemm_tc_kernel ({top}, all shapes)", "bound": "tensor", "achieved": ach,
+            passes, rate = MODE_COST[precision]
+            roofline = {"kernel": "gemm_tc_kernel (dense layers: fwd + dgrad + wgrad, all shapes)", "bound": "tensor", "achieved": ach,
                         "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
                         "peak_source": f"{pk_src} dense bf16 GEMM (sustained)",
                         "mode": f"{precision}: {passes} tcgen05 pass(es) per product at {rate}x the bf16 rate; achieved counts "
@@ -487,7 +507,7 @@ def main():
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": f"{pk_src} copy bandwidth"}
         try:                                               # never let a reporting extra take the bench down
-            passes_, rate_ = {"fp32": (3, 0.5), "bf16x3": (3, 1.0), "bf16": (1, 1.0), "tf32": (1, 0.5)}[precision]
+            passes_, rate_ = MODE_COST[precision]
             roofline["path"] = path_roofline(summ, 2, pk["hbm_gbs"], bf16_peak, passes_, rate_)
             roofline["path"]["frac_of_timed_step"] = roofline["path"]["roofline_ms_per_step"] / (ms / K)
             roofline["path"]["frac_of_timed_step_mode_ceiling"] = \
@@ -523,7 +543,8 @@ def main():
             "metric": "mesh vertices/sec fwd" if infer else "mesh vertices/sec fwd+bwd", "value": value,
             "unit": "vertices/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16_1pass": "bf16", "tf32": "tf32"}[args.dtype], "data": "synthetic",
+            "dtype": {"fp32": "f32", "f16": "f16", "bf16": "f16", "bf16x3": "bf16", "bf16_1pass": "bf16", "tf32": "tf32",
+                      "tf32x3": "f32"}[args.dtype], "data": "synthetic",
             "config": {"workload": wl["name"], "vertices_per_step_per_gpu": n0,
                        "step": "graph-structure (CSR) build + forward (eval, no_grad)" if infer else
                                "graph-structure (CSR) build + forward + masked L1 + backward"

@@ -200,6 +200,36 @@ int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t l
                        const int32_t* gid, const float* mean, const float* rstd, int act, float* dx, int64_t lddx,
                        float* amax_out, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
 
+/* ---- affine segmented norms: the alternative norm_type modules of the network and the BatchNorm1d
+ * over the EDGES inside SingleConvMeshNet's message MLP, all of the form
+ *     y = gamma * (x - alpha * m[g]) * r[g] + beta,   r = 1 / sqrt(v + eps),   m = slice sum / cnt
+ *   kind 0: v = slice sum of (x - m)^2 / cnt    -- torch_geometric BatchNorm == nn.BatchNorm1d over node rows
+ *           (models/surfacetextureinpaintingnet.py:236-241 BatchNorm2Param; edge_conv_filter.py:34-44), one slice = the batch
+ *   kind 1: v = slice sum of x^2 / cnt          -- SingleBatchGraphNorm (models/modules/singlebatchgroupnorm.py:44-71), which
+ *           takes the second moment of the UN-shifted x (:66-68); slices = the reference's linspace slices, cnt = their length
+ * alpha / gamma / beta are per-channel parameters (NULL: 1 / 1 / 0).  Statistics are the deterministic two-stage column
+ * reductions of stinet_segnorm_stats (no atomics).  gid (int32 per row -> segment; NULL only with one segment).
+ *   fwd    writes y, mean[n_seg, C], rstd[n_seg, C]
+ *   apply  the elementwise part alone, with given statistics (eval mode: running mean / 1/sqrt(running_var + eps))
+ *   bwd    dx, dgamma = sum dy (x - alpha m) r, dbeta = sum dy, dalpha = -gamma sum_s m r sum_slice dy  (any of the four
+ *          outputs may be NULL); requires every row's gid to be the slice that contains it
+ *   bn_running_update  running_mean / running_var of nn.BatchNorm1d after one training step (unbiased variance) */
+size_t stinet_affnorm_workspace_bytes(int64_t max_seg_rows, int64_t channels, int64_t n_seg);
+int stinet_affnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg, int64_t max_seg_rows,
+                       const int32_t* slice_ptr, const float* cnt, const int32_t* gid, int kind, float eps,
+                       const float* alpha, const float* gamma, const float* beta, float* out, int64_t ldo, float* mean,
+                       float* rstd, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+int stinet_affnorm_apply(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, const int32_t* gid,
+                         const float* mean, const float* rstd, const float* alpha, const float* gamma, const float* beta,
+                         float* out, int64_t ldo, stinet_stream_t stream);
+int stinet_affnorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t ldg, int64_t n_rows, int64_t channels,
+                       int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, const int32_t* gid,
+                       int kind, const float* mean, const float* rstd, const float* alpha, const float* gamma, float* dx,
+                       int64_t lddx, float* dgamma, float* dbeta, float* dalpha, void* workspace, size_t workspace_bytes,
+                       stinet_stream_t stream);
+int stinet_bn_running_update(const float* mean, const float* rstd, int64_t n_rows, float eps, float momentum,
+                             int64_t channels, float* running_mean, float* running_var, stinet_stream_t stream);
+
 /* ---- dense layers (replace torch.nn.Linear inside the message MLP, the shortcut and the head:
  * models/modules/edge_conv_filter.py:46-55, models/surfacetextureinpaintingnet.py:504-505,356-358).
  * fwd:   C[M,N]  = A[M,K] W[N,K]^T + bias[N] * (rowmask ? rowmask[m] > 0 : 1)

@@ -627,6 +627,139 @@ static void launch_colreduce(bool vec, const NormArgs& a, int64_t n_seg, cudaStr
   else K(seg_colreduce_kernel<MODE, false><<<grid, kNormThreads, 0, s>>>(a));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// affine segmented norms: BatchNorm over the node rows (BatchNorm2Param, nn.BatchNorm1d inside the
+// with_norm message MLP) and SingleBatchGraphNorm share one form
+//     y = gamma * (x - alpha * m[g]) * r[g] + beta,   r = 1 / sqrt(v + eps)
+// with m = slice mean, and v = slice mean of (x - m)^2 (kind 0, batch norm) or of x^2 (kind 1: the reference's GraphNorm
+// takes the second moment of the UN-shifted x, singlebatchgroupnorm.py:66-68).  Statistics come from the deterministic
+// column reductions above; the kernels below are the elementwise apply, its backward and the parameter gradients.
+
+template <bool VEC>
+__global__ void __launch_bounds__(kNormThreads)
+affnorm_apply_kernel(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int channels, const int32_t* __restrict__ gid,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ alpha,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out, int64_t ldo) {
+  constexpr int W = VEC ? 4 : 1;
+  const int groups = channels / W;
+  const int64_t total = n_rows * groups;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / groups;
+    const int grp = (int)(idx - r * groups);
+    const int g = gid ? gid[r] : 0;
+    float v[W], o[W];
+    if (VEC) {
+      const float4 t = reinterpret_cast<const float4*>(x + r * ldx)[grp];
+      v[0] = t.x; v[1 % W] = t.y; v[2 % W] = t.z; v[3 % W] = t.w;
+    } else {
+      v[0] = x[r * ldx + grp];
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int c = grp * W + w;
+      const int64_t sc = (int64_t)g * channels + c;
+      const float u = v[w] - (alpha ? alpha[c] : 1.f) * mean[sc];
+      o[w] = (gamma ? gamma[c] : 1.f) * u * rstd[sc] + (beta ? beta[c] : 0.f);
+    }
+    if (VEC) reinterpret_cast<float4*>(out + r * ldo)[grp] = make_float4(o[0], o[1 % W], o[2 % W], o[3 % W]);
+    else out[r * ldo + grp] = o[0];
+  }
+}
+
+// am[s,c] = alpha[c] * mean[s,c] (the shift the reductions of the backward centre x with); ones[s] = 1
+__global__ void affnorm_prep_kernel(const float* __restrict__ mean, const float* __restrict__ alpha, int n_seg, int channels,
+                                    float* __restrict__ am, float* __restrict__ ones) {
+  const int64_t total = (int64_t)n_seg * channels;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+    am[idx] = (alpha ? alpha[idx % channels] : 1.f) * mean[idx];
+  if (blockIdx.x == 0)
+    for (int sidx = threadIdx.x; sidx < n_seg; sidx += blockDim.x) ones[sidx] = 1.f;
+}
+
+// dx_i = r gamma dy_i - alpha r gamma T1 / n - r^3 gamma T2 w_i / n,  w_i = x_i - m (kind 0) or x_i (kind 1),
+// T1 = sum_slice dy, T2 = sum_slice dy (x - alpha m), n = the forward's divisor of the slice
+template <bool VEC>
+__global__ void __launch_bounds__(kNormThreads)
+affnorm_bwd_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t ldg, int64_t n_rows,
+                         int channels, const int32_t* __restrict__ gid, const float* __restrict__ cnt, int kind,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ alpha,
+                         const float* __restrict__ gamma, const float* __restrict__ t1, const float* __restrict__ t2,
+                         float* __restrict__ dx, int64_t lddx) {
+  constexpr int W = VEC ? 4 : 1;
+  const int groups = channels / W;
+  const int64_t total = n_rows * groups;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / groups;
+    const int grp = (int)(idx - r * groups);
+    const int g = gid ? gid[r] : 0;
+    const float n = cnt[g];
+    float v[W], d[W], o[W];
+    if (VEC) {
+      const float4 t = reinterpret_cast<const float4*>(x + r * ldx)[grp];
+      v[0] = t.x; v[1 % W] = t.y; v[2 % W] = t.z; v[3 % W] = t.w;
+      const float4 q = reinterpret_cast<const float4*>(dy + r * ldg)[grp];
+      d[0] = q.x; d[1 % W] = q.y; d[2 % W] = q.z; d[3 % W] = q.w;
+    } else {
+      v[0] = x[r * ldx + grp];
+      d[0] = dy[r * ldg + grp];
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int c = grp * W + w;
+      const int64_t sc = (int64_t)g * channels + c;
+      const float rs = rstd[sc], gm = gamma ? gamma[c] : 1.f, al = alpha ? alpha[c] : 1.f;
+      const float wi = kind == 0 ? v[w] - mean[sc] : v[w];
+      o[w] = rs * gm * (d[w] - al * t1[sc] / n - rs * rs * t2[sc] * wi / n);
+    }
+    if (VEC) reinterpret_cast<float4*>(dx + r * lddx)[grp] = make_float4(o[0], o[1 % W], o[2 % W], o[3 % W]);
+    else dx[r * lddx + grp] = o[0];
+  }
+}
+
+// dgamma[c] = sum_s r T2, dbeta[c] = sum_s T1, dalpha[c] = -gamma sum_s m r T1   (segments in ascending order)
+__global__ void affnorm_param_grads_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
+                                           const float* __restrict__ gamma, const float* __restrict__ t1,
+                                           const float* __restrict__ t2, int n_seg, int channels, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta, float* __restrict__ dalpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  float g = 0.f, b = 0.f, a = 0.f;
+  for (int sidx = 0; sidx < n_seg; ++sidx) {
+    const int64_t sc = (int64_t)sidx * channels + c;
+    g += rstd[sc] * t2[sc];
+    b += t1[sc];
+    a += mean[sc] * rstd[sc] * t1[sc];
+  }
+  if (dgamma) dgamma[c] = g;
+  if (dbeta) dbeta[c] = b;
+  if (dalpha) dalpha[c] = -(gamma ? gamma[c] : 1.f) * a;
+}
+
+// running statistics of nn.BatchNorm1d after one training step: mean as is, variance unbiased (n / (n - 1))
+__global__ void bn_running_update_kernel(const float* __restrict__ mean, const float* __restrict__ rstd, float n, float eps,
+                                         float momentum, int channels, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  const float rs = rstd[c];
+  const float var = 1.f / (rs * rs) - eps;
+  const float unbiased = n > 1.f ? var * (n / (n - 1.f)) : var;
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean[c];
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+}
+
+struct AffWs { NormWs n; float* am; float* ones; size_t bytes; };
+static AffWs carve_aff(void* base, int64_t max_seg_rows, int64_t channels, int64_t n_seg) {
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  AffWs w;
+  w.n = carve_norm(base, max_seg_rows, channels, n_seg);
+  char* p = static_cast<char*>(base) + up(w.n.bytes);
+  w.am = reinterpret_cast<float*>(p);
+  w.ones = reinterpret_cast<float*>(p + up(sizeof(float) * (size_t)n_seg * channels));
+  w.bytes = up(w.n.bytes) + up(sizeof(float) * (size_t)n_seg * channels) + up(sizeof(float) * (size_t)n_seg);
+  return w;
+}
+
 }  // namespace stinet
 
 using namespace stinet;
@@ -770,4 +903,102 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
   int rc = check_launch("segnorm_bwd");
   if (rc == STINET_OK && amax_out != nullptr) rc = stinet_f16_amax(dx, lddx, n_rows, channels, amax_out, stream_);
   return rc;
+}
+
+// ---- affine segmented norms ------------------------------------------------------------------------------------
+
+extern "C" size_t stinet_affnorm_workspace_bytes(int64_t max_seg_rows, int64_t channels, int64_t n_seg) {
+  if (max_seg_rows < 0 || channels <= 0 || n_seg <= 0) return 0;
+  return carve_aff(nullptr, max_seg_rows, channels, n_seg).bytes;
+}
+
+extern "C" int stinet_affnorm_apply(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, const int32_t* gid,
+                                    const float* mean, const float* rstd, const float* alpha, const float* gamma,
+                                    const float* beta, float* out, int64_t ldo, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && mean && rstd && out, STINET_ERR_ARG, "affnorm_apply: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldx >= channels && ldo >= channels, STINET_ERR_ARG, "affnorm_apply: bad shape");
+  if (n_rows == 0) return STINET_OK;
+  const bool vec = nvec(channels, {x, out}, {ldx, ldo});
+  const int grid = wave_grid(n_rows * (channels / (vec ? 4 : 1)), kNormThreads * 4, 8, 8);
+  if (vec) K(affnorm_apply_kernel<true><<<grid, kNormThreads, 0, s>>>(x, ldx, n_rows, (int)channels, gid, mean, rstd, alpha, gamma, beta, out, ldo));
+  else K(affnorm_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, n_rows, (int)channels, gid, mean, rstd, alpha, gamma, beta, out, ldo));
+  return check_launch("affnorm_apply");
+}
+
+extern "C" int stinet_affnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
+                                  int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, const int32_t* gid,
+                                  int kind, float eps, const float* alpha, const float* gamma, const float* beta,
+                                  float* out, int64_t ldo, float* mean, float* rstd, void* workspace,
+                                  size_t workspace_bytes, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && slice_ptr && cnt && out && mean && rstd, STINET_ERR_ARG, "affnorm_fwd: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && channels > 0 && n_seg > 0 && n_seg <= 65535 && ldx >= channels && ldo >= channels &&
+                     (kind == 0 || kind == 1) && (n_seg == 1 || gid),
+                 STINET_ERR_ARG, "affnorm_fwd: bad shape / kind (several segments need gid)");
+  AffWs w = carve_aff(workspace, max_seg_rows, channels, n_seg);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "affnorm_fwd: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  const bool vec = nvec(channels, {x}, {ldx});
+  const dim3 fin_grid((unsigned)ceil_div(channels, 32), (unsigned)n_seg);
+  NormArgs a{x, ldx, nullptr, 0, slice_ptr, nullptr, nullptr, nullptr, w.n.part0, w.n.part1, (int)channels, w.n.max_chunks, 0};
+  launch_colreduce<MODE_SUM>(vec, a, n_seg, s);
+  K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.n.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.n.max_chunks, eps, mean));
+  if (kind == 0) {
+    a.mean = mean;                                   // centred second moment
+  } else {
+    cudaError_t e = cudaMemsetAsync(w.am, 0, sizeof(float) * (size_t)n_seg * channels, s);   // second moment of x itself
+    STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "affnorm_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    a.mean = w.am;
+  }
+  launch_colreduce<MODE_CSQ>(vec, a, n_seg, s);
+  K(seg_finalize_kernel<1><<<fin_grid, 1024, 0, s>>>(w.n.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.n.max_chunks, eps, rstd));
+  int rc = check_launch("affnorm_fwd");
+  if (rc != STINET_OK) return rc;
+  return stinet_affnorm_apply(x, ldx, n_rows, channels, n_seg == 1 ? nullptr : gid, mean, rstd, alpha, gamma, beta, out, ldo, stream_);
+}
+
+extern "C" int stinet_affnorm_bwd(const float* x, int64_t ldx, const float* dy, int64_t ldg, int64_t n_rows,
+                                  int64_t channels, int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr,
+                                  const float* cnt, const int32_t* gid, int kind, const float* mean, const float* rstd,
+                                  const float* alpha, const float* gamma, float* dx, int64_t lddx, float* dgamma,
+                                  float* dbeta, float* dalpha, void* workspace, size_t workspace_bytes,
+                                  stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(x && dy && slice_ptr && cnt && mean && rstd, STINET_ERR_ARG, "affnorm_bwd: null pointer");
+  STINET_REQUIRE(n_rows >= 0 && channels > 0 && n_seg > 0 && n_seg <= 65535 && ldx >= channels && ldg >= channels &&
+                     (!dx || lddx >= channels) && (kind == 0 || kind == 1) && (n_seg == 1 || gid),
+                 STINET_ERR_ARG, "affnorm_bwd: bad shape / kind (several segments need gid)");
+  AffWs w = carve_aff(workspace, max_seg_rows, channels, n_seg);
+  STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "affnorm_bwd: workspace %zu < %zu",
+                 workspace_bytes, w.bytes);
+  // T1 = sum_slice dy, T2 = sum_slice dy (x - alpha m): the backward column reduction with shift alpha*m and unit scale
+  K(affnorm_prep_kernel<<<wave_grid(n_seg * channels, 256, 8), 256, 0, s>>>(mean, alpha, (int)n_seg, (int)channels, w.am, w.ones));
+  const bool vec = nvec(channels, {x, dy}, {ldx, ldg});
+  NormArgs a{x, ldx, dy, ldg, slice_ptr, nullptr, w.am, nullptr, w.n.part0, w.n.part1, (int)channels, w.n.max_chunks, STINET_ACT_NONE};
+  launch_colreduce<MODE_BWD>(vec, a, n_seg, s);
+  const dim3 fin_grid((unsigned)ceil_div(channels, 32), (unsigned)n_seg);
+  K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.n.part0, slice_ptr, w.ones, (int)n_seg, (int)channels, w.n.max_chunks, 0.f, w.n.s1));
+  K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.n.part1, slice_ptr, w.ones, (int)n_seg, (int)channels, w.n.max_chunks, 0.f, w.n.s2));
+  if (dx != nullptr && n_rows > 0) {
+    const bool v2 = nvec(channels, {x, dy, dx}, {ldx, ldg, lddx});
+    const int grid = wave_grid(n_rows * (channels / (v2 ? 4 : 1)), kNormThreads * 4, 8, 8);
+    const int32_t* g = n_seg == 1 ? nullptr : gid;
+    if (v2) K(affnorm_bwd_apply_kernel<true><<<grid, kNormThreads, 0, s>>>(x, ldx, dy, ldg, n_rows, (int)channels, g, cnt, kind, mean, rstd, alpha, gamma, w.n.s1, w.n.s2, dx, lddx));
+    else K(affnorm_bwd_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, dy, ldg, n_rows, (int)channels, g, cnt, kind, mean, rstd, alpha, gamma, w.n.s1, w.n.s2, dx, lddx));
+  }
+  if (dgamma || dbeta || dalpha)
+    K(affnorm_param_grads_kernel<<<(unsigned)ceil_div(channels, 128), 128, 0, s>>>(mean, rstd, gamma, w.n.s1, w.n.s2, (int)n_seg,
+                                                                                  (int)channels, dgamma, dbeta, dalpha));
+  return check_launch("affnorm_bwd");
+}
+
+extern "C" int stinet_bn_running_update(const float* mean, const float* rstd, int64_t n_rows, float eps, float momentum,
+                                        int64_t channels, float* running_mean, float* running_var, stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(mean && rstd && running_mean && running_var, STINET_ERR_ARG, "bn_running_update: null pointer");
+  STINET_REQUIRE(channels > 0 && n_rows >= 0, STINET_ERR_ARG, "bn_running_update: bad shape");
+  K(bn_running_update_kernel<<<(unsigned)ceil_div(channels, 128), 128, 0, s>>>(mean, rstd, (float)n_rows, eps, momentum, (int)channels,
+                                                                             running_mean, running_var));
+  return check_launch("bn_running_update");
 }

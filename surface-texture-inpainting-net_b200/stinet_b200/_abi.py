@@ -46,6 +46,11 @@ SIGNATURES = {
     "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, P, SZ, P]),
     "stinet_segnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, I64, P]),
     "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, P, SZ, P]),
+    "stinet_affnorm_workspace_bytes": (SZ, [I64, I64, I64]),
+    "stinet_affnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, P, I, F, P, P, P, P, I64, P, P, P, SZ, P]),
+    "stinet_affnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, P, P, P, I64, P]),
+    "stinet_affnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I, P, P, P, P, P, I64, P, P, P, P, SZ, P]),
+    "stinet_bn_running_update": (I, [P, P, I64, F, F, I64, P, P, P]),
     "stinet_metrics_workspace_bytes": (SZ, [I64]),
     "stinet_graph_laplace": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_graph_laplace_variance": (I, [P, I64, P, P, I64, P, P, SZ, P]),

@@ -108,10 +108,10 @@ def get_gcn_filter(input_size: int, output_size, activation: torch.nn.Module = t
         # reference :34-44 -- no biases, BatchNorm1d over the edge dimension after each Linear
         inner_module = Seq(
             Lin(double_input_size, 2 * output_size, bias=False),
-            torch.nn.BatchNorm1d(2 * output_size),
+            ops.BatchNorm1d(2 * output_size),
             activation(inplace=inplace),
             Lin(2 * output_size, output_size, bias=False),
-            torch.nn.BatchNorm1d(output_size),
+            ops.BatchNorm1d(output_size),
         )
         return module(inner_module, aggr=aggregation)
     if activation is not torch.nn.ReLU:

@@ -7,7 +7,8 @@ those blocks' running statistics receive two momentum updates per training step.
 
 The per-edge MLP cannot be hoisted to the vertices here (its statistics are over edges), so this network exercises
 the literal path of stinet_b200.models.modules.edge_conv_filter.EdgeConv: row gathers and segmented sums on the
-pooling kernels, Linears as tcgen05 GEMMs over E rows; BatchNorm1d / ReLU / cat are device tensor ops.
+pooling kernels, Linears as tcgen05 GEMMs over E rows, BatchNorm1d on the segmented-reduction kernels (ops.BatchNorm1d),
+the skip concatenation written in place by the unpool kernel (ops.unpool_concat); ReLU is a device tensor op.
 
 Reference quirk kept: ResBlock adds the residual in place onto a ReLU output (:107), which makes the reference's own
 backward raise for num_propagation_steps > 1; the sum is written out of place here (same values), so more than one
@@ -52,7 +53,7 @@ class SingleConvMeshNet(torch.nn.Module):
                 decoders.append(self.ResBlock(stack(width + widths[level + 1], width), self._act))   # skip || unpooled (:58)
             encoders.append(self.ResBlock(enc, self._act))
             din = width
-        head = Seq(Lin(widths[0], widths[0] // 2), BatchNorm1d(widths[0] // 2), self._activation(inplace=False),
+        head = Seq(Lin(widths[0], widths[0] // 2), ops.BatchNorm1d(widths[0] // 2), self._activation(inplace=False),
                    Lin(widths[0] // 2, num_classes))
         self.left_geo_cnns = torch.nn.ModuleList(encoders)
         self.right_geo_cnns = torch.nn.ModuleList(decoders)
@@ -111,8 +112,8 @@ class SingleConvMeshNet(torch.nn.Module):
             levels.append(run(self.left_geo_cnns[level], curr, edges(level)))
         current = levels[-1]
         for level in range(1, G):                   # decoder
-            back = ops.unpool(current, cache.cluster(G - level))
-            fused = torch.cat((levels[-(level + 1)], back), -1)
+            # [skip || unpooled] (:140-141): the gather kernel writes its rows straight into the right-hand columns
+            fused = ops.unpool_concat(levels[-(level + 1)], current, cache.cluster(G - level))
             if level == G - 1:
                 fused = self.right_geo_cnns[-level](fused, edges(0))
             else:

@@ -7,7 +7,9 @@ Differences that are deliberate and numerically neutral:
   * graph structure (CSR per edge set, cluster CSR per trace map, per-level norm segments) is built once per batch
     by GraphCache instead of being re-derived inside every layer; the only host read is `num_vertices` ([B, L+1] ints);
   * torch.utils.checkpoint (:429,:438,:451-455) is accepted but not applied: on a 180 GB part the activations fit,
-    and recomputation only costs time (the reference states the block is deterministic, :509);
+    and recomputation only costs time (the reference states the block is deterministic, :509).  Its one observable
+    side effect -- a BatchNorm inside a checkpointed block updates its running statistics twice per step -- is
+    reproduced (BatchNorm1d.updates_per_step);
   * the per-level graph id is obtained by max-pooling ids through the traces in the encoder (as :422) and re-used
     in the decoder instead of `batch.index_select(0, trace)` (:447) -- identical whenever a trace map stays inside
     its own graph, which HierarchicalData's offsets guarantee.
@@ -30,12 +32,12 @@ from .modules.singlebatchgroupnorm import SingleBatchGraphNorm
 
 
 class BatchNorm2Param(nn.Module):
-    """reference :236-241 -- torch_geometric BatchNorm (BatchNorm1d over node rows) that ignores `batch`.
-    Round-1 status: ATen BatchNorm1d on the device, not used by the shipped configs."""
+    """reference :236-241 -- torch_geometric BatchNorm (BatchNorm1d over node rows) that ignores `batch`.  Evaluated by the
+    segmented-reduction kernels (ops.BatchNorm1d -> stinet_affnorm_*): deterministic, same state_dict keys (`module.*`)."""
 
     def __init__(self, in_channels, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
         super().__init__()
-        self.module = nn.BatchNorm1d(in_channels, eps, momentum, affine, track_running_stats)
+        self.module = ops.BatchNorm1d(in_channels, eps, momentum, affine, track_running_stats)
 
     def forward(self, input, batch=None):
         return self.module(input)
@@ -154,6 +156,15 @@ class SurfaceTextureInpaintingNet(nn.Module):
                 if hasattr(m, 'bias') and m.bias is not None:
                     nn.init.zeros_(m.bias)
         self.apply(init_weights)
+        # blocks the reference wraps in torch.utils.checkpoint (:429, :436-438, :451-455) run their forward twice per
+        # training step, so a BatchNorm inside them takes two momentum updates; nothing is recomputed here (180 GB of
+        # HBM), the second update is applied directly
+        twice = list(self.encoder_blocks) + list(self.decoder_blocks)
+        if self.checkpoint_bottleneck:
+            twice += [b for i, b in enumerate(self.bottleneck_blocks) if (i + 1) % self.num_blocks_per_uncheckpointed_block == 0]
+        for b in twice:
+            if isinstance(b.first_norm, BatchNorm2Param):
+                b.first_norm.module.updates_per_step = 2
         self.set_precision(precision)
 
     def set_precision(self, precision: str):

@@ -627,6 +627,42 @@ class UnpoolFn(Function):
         return dxc, None
 
 
+class UnpoolConcatFn(Function):
+    """out = [skip || coarse[trace]]  (reference models/singleconvmeshnet.py:140-141): the row gather writes into the column
+    slice [Ca, Ca+Cb) of the pre-allocated buffer (`ldo` of stinet_unpool_fwd); backward reads the same slice in place."""
+
+    @staticmethod
+    def forward(ctx, skip, xc, cl: ClusterCSR):
+        skip, xc = _mat(skip), _mat(xc)
+        n, ca = skip.shape
+        nc, cb = xc.shape
+        assert n == cl.n_fine and nc == cl.n_coarse
+        out = torch.empty((n, ca + cb), dtype=torch.float32, device=xc.device)
+        out[:, :ca].copy_(skip)
+        _abi.call("stinet_unpool_fwd", xc.data_ptr(), _ld(xc), cl.trace32.data_ptr(), n, cb, out.data_ptr() + 4 * ca, ca + cb,
+                  _stream(), cost=(n * (4 + 8 * cb), 0, f"C{cb}"))
+        ctx.cl, ctx.ca, ctx.cb = cl, ca, cb
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        cl, ca, cb = ctx.cl, ctx.ca, ctx.cb
+        g = _mat(g)
+        dskip = g[:, :ca] if ctx.needs_input_grad[0] else None
+        dxc = None
+        if ctx.needs_input_grad[1]:
+            dxc = torch.empty((cl.n_coarse, cb), dtype=torch.float32, device=g.device)
+            _abi.call("stinet_unpool_bwd", g.data_ptr() + 4 * ca, _ld(g), cl.rowptr.data_ptr(), cl.member.data_ptr(),
+                      cl.n_coarse, cb, dxc.data_ptr(), cb, _stream(),
+                      cost=(cl.n_fine * (4 * cb + 4) + cl.n_coarse * 4 * cb, 0, f"C{cb}"))
+        return dskip, dxc, None
+
+
+def unpool_concat(skip, xc, cl):
+    return UnpoolConcatFn.apply(skip, xc, cl)
+
+
 def _carry_amax(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     """max / mean pooling and row gathers cannot raise max|x|: the source's bound serves the result's operand planes."""
     known = getattr(src, "_stinet_amax", None)
@@ -767,3 +803,110 @@ def norm_act_res(x, residual, seg, use_norm=True, act=ACT_ELU, eps=1e-5):
         set_amax(out, NormActResFn.last_amax)        # max|out| came with the norm kernels: no reduction pass later
         NormActResFn.last_amax = None
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# affine segmented norms: BatchNorm over rows, SingleBatchGraphNorm
+
+
+class AffNormFn(Function):
+    """y = gamma * (x - alpha * m[g]) * r[g] + beta with slice statistics (kind 0: centred variance -- BatchNorm; kind 1:
+    second moment of x itself -- the reference's SingleBatchGraphNorm).  Returns (y, mean, rstd); the statistics are
+    non-differentiable by-products (BatchNorm's running-stat update reads them)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, gamma, beta, slice_ptr, cnt, gid, n_seg: int, max_seg_rows: int, kind: int, eps: float):
+        x = _mat(x)
+        n, c = x.shape
+        dev = x.device
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+        mean = torch.empty((n_seg, c), dtype=torch.float32, device=dev)
+        rstd = torch.empty((n_seg, c), dtype=torch.float32, device=dev)
+        nb = _abi.query("stinet_affnorm_workspace_bytes", max_seg_rows, c, n_seg)
+        ws = _ws(nb, dev)
+        _abi.call("stinet_affnorm_fwd", x.data_ptr(), _ld(x), n, c, n_seg, max_seg_rows, slice_ptr.data_ptr(), cnt.data_ptr(),
+                  _ptr(gid), kind, float(eps), _ptr(alpha), _ptr(gamma), _ptr(beta), out.data_ptr(), c, mean.data_ptr(),
+                  rstd.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(4 * n * c * 4, 8 * n * c, f"C{c}"))
+        ctx.save_for_backward(x, mean, rstd, alpha, gamma, slice_ptr, cnt, gid)
+        ctx.cfg = (n_seg, max_seg_rows, kind)
+        ctx.mark_non_differentiable(mean, rstd)
+        return out, mean, rstd
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _dm, _dr):
+        x, mean, rstd, alpha, gamma, slice_ptr, cnt, gid = ctx.saved_tensors
+        n_seg, max_seg_rows, kind = ctx.cfg
+        dy = _mat(dy)
+        n, c = x.shape
+        dev = x.device
+        need = ctx.needs_input_grad
+        dx = torch.empty((n, c), dtype=torch.float32, device=dev) if need[0] else None
+        dal = torch.empty((c,), dtype=torch.float32, device=dev) if (alpha is not None and need[1]) else None
+        dga = torch.empty((c,), dtype=torch.float32, device=dev) if (gamma is not None and need[2]) else None
+        dbe = torch.empty((c,), dtype=torch.float32, device=dev) if need[3] else None
+        nb = _abi.query("stinet_affnorm_workspace_bytes", max_seg_rows, c, n_seg)
+        ws = _ws(nb, dev)
+        _abi.call("stinet_affnorm_bwd", x.data_ptr(), _ld(x), dy.data_ptr(), _ld(dy), n, c, n_seg, max_seg_rows,
+                  slice_ptr.data_ptr(), cnt.data_ptr(), _ptr(gid), kind, mean.data_ptr(), rstd.data_ptr(), _ptr(alpha),
+                  _ptr(gamma), _ptr(dx), c, _ptr(dga), _ptr(dbe), _ptr(dal), ws.data_ptr(), nb, _stream(),
+                  cost=(4 * n * c * 5, 12 * n * c, f"C{c}"))
+        return dx, dal, dga, dbe, None, None, None, None, None, None, None
+
+
+class AffNormEvalFn(Function):
+    """y = gamma * (x - mean) * rstd + beta with GIVEN statistics (BatchNorm in eval mode)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, rstd):
+        x = _mat(x)
+        n, c = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        _abi.call("stinet_affnorm_apply", x.data_ptr(), _ld(x), n, c, None, mean.data_ptr(), rstd.data_ptr(), None,
+                  _ptr(gamma), _ptr(beta), out.data_ptr(), c, _stream(), cost=(8 * n * c, 3 * n * c, f"C{c}"))
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        # statistics are constants here: three short tensor expressions (eval-mode gradients are not on the hot path)
+        x, gamma, mean, rstd = ctx.saved_tensors
+        xh = (x - mean) * rstd
+        g = gamma if gamma is not None else 1.0
+        return dy * (g * rstd), ((dy * xh).sum(0) if gamma is not None else None), dy.sum(0), None, None
+
+
+def batch_norm(x, weight, bias, running_mean, running_var, training: bool, momentum: float, eps: float, updates: int = 1):
+    """nn.BatchNorm1d over the rows of x [N, C] on the segmented-reduction kernels (deterministic; replaces
+    F.batch_norm).  Updates the running statistics in place when training (unbiased variance, like torch); `updates` = 2
+    reproduces a block the reference wraps in torch.utils.checkpoint, whose forward -- and momentum update -- runs twice."""
+    n, c = x.shape
+    if not training and running_mean is not None:
+        rstd = torch.rsqrt(running_var + eps).reshape(1, c).contiguous()
+        return AffNormEvalFn.apply(x, weight, bias, running_mean.reshape(1, c).contiguous(), rstd)
+    from .graph import _segment_tables
+    slice_ptr, cnt = _segment_tables((0, n), (max(n, 1),), x.device)
+    out, mean, rstd = AffNormFn.apply(x, None, weight, bias, slice_ptr, cnt, None, 1, n, 0, eps)
+    if training and running_mean is not None:
+        for _ in range(updates):
+            _abi.call("stinet_bn_running_update", mean.data_ptr(), rstd.data_ptr(), n, float(eps), float(momentum), c,
+                      running_mean.data_ptr(), running_var.data_ptr(), _stream())
+    return out
+
+
+class BatchNorm1d(torch.nn.BatchNorm1d):
+    """nn.BatchNorm1d (same parameters, buffers and state_dict keys) evaluated by ops.batch_norm on CUDA inputs."""
+
+    updates_per_step = 1      # 2: the reference runs this module inside torch.utils.checkpoint (forward + recomputation)
+
+    def forward(self, input):
+        if not input.is_cuda or input.dim() != 2 or self.momentum is None:
+            return super().forward(input)
+        training = self.training or self.running_mean is None
+        # the recomputation only happens when a backward pass will run
+        updates = self.updates_per_step if (torch.is_grad_enabled() and input.requires_grad) else 1
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(updates)
+        return batch_norm(input, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
+                          self.running_var if self.track_running_stats else None, training, self.momentum, self.eps, updates)

@@ -351,3 +351,98 @@ def test_edge_message_mask_kernels_equal_recomputing_kernels(kind, h):
     _abi.call("stinet_edge_message_bwd_source_mask", dh.data_ptr(), h, csr.rowptr_t.data_ptr(), rs.data_ptr(),
               cs.data_ptr(), tpos.data_ptr(), mask.data_ptr(), n, h, d1.data_ptr() + 4 * h, 2 * h, s)
     assert torch.equal(d0, d1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# affine segmented norms and the in-place skip concatenation of the unpool kernel (row a8)
+
+
+@pytest.mark.parametrize("n,c", [(1000, 16), (4097, 64), (333, 10), (20000, 128)])
+def test_batch_norm_kernels_match_torch(n, c):
+    """ops.BatchNorm1d (stinet_affnorm_*, kind 0) against nn.BatchNorm1d in fp64: output, gradients of x / weight / bias,
+    running statistics after the step (unbiased variance), then eval mode on the updated statistics."""
+    from stinet_b200 import ops
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, c, generator=g) * 3 + torch.randn(c, generator=g)
+    go = torch.randn(n, c, generator=g)
+    ref = torch.nn.BatchNorm1d(c).double()
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(c, generator=g))
+        ref.bias.copy_(torch.randn(c, generator=g))
+    bn = ops.BatchNorm1d(c)
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in ref.state_dict().items()})
+    bn = bn.to(DEV)
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(go.double())
+    xd = x.to(DEV).requires_grad_(True)
+    yd = bn(xd)
+    yd.backward(go.to(DEV))
+    assert rel_err(yd, yr) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= TOL
+    assert rel_err(bn.weight.grad, ref.weight.grad) <= TOL and rel_err(bn.bias.grad, ref.bias.grad) <= TOL
+    assert rel_err(bn.running_mean, ref.running_mean) <= TOL and rel_err(bn.running_var, ref.running_var) <= TOL
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+    ref.eval(), bn.eval()
+    with torch.no_grad():
+        assert rel_err(bn(xd), ref(xr)) <= TOL
+    # run-to-run bit determinism (no atomics anywhere in the reductions)
+    bn.train()
+    assert torch.equal(bn(xd), bn(xd))
+
+
+@pytest.mark.parametrize("counts", [None, [500, 500, 500], [64, 64]])
+@pytest.mark.parametrize("c", [8, 40, 130])
+def test_graph_norm_kernels_match_the_reference_formula(counts, c):
+    """SingleBatchGraphNorm on the kernels (stinet_affnorm_*, kind 1) against the reference's formula evaluated in fp64
+    (models/modules/singlebatchgroupnorm.py:44-71, incl. the un-shifted second moment): output and the gradients of x,
+    weight, bias and mean_scale."""
+    from stinet_b200.models.modules.singlebatchgroupnorm import SingleBatchGraphNorm
+    n = sum(counts) if counts else 777
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, c, generator=g) * 2 + 0.7
+    go = torch.randn(n, c, generator=g)
+    batch = None if counts is None else torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts))
+    mod = SingleBatchGraphNorm(c)
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.copy_(torch.randn(c, generator=g))
+    w, b, ms = (p.detach().double().requires_grad_(True) for p in (mod.weight, mod.bias, mod.mean_scale))
+    xr = x.double().requires_grad_(True)
+    bsz = 1 if counts is None else len(counts)
+    ptr = torch.linspace(0, n, bsz + 1, dtype=torch.int)
+    bvec = torch.zeros(n, dtype=torch.long) if batch is None else batch
+    mean = torch.stack([xr[ptr[i]:ptr[i + 1]].mean(0) for i in range(bsz)]).index_select(0, bvec)
+    var = torch.stack([xr[ptr[i]:ptr[i + 1]].pow(2).mean(0) for i in range(bsz)])
+    yr = w * (xr - mean * ms) / (var + mod.eps).sqrt().index_select(0, bvec) + b
+    yr.backward(go.double())
+    mod = mod.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    yd = mod(xd, None if batch is None else batch.to(DEV))
+    yd.backward(go.to(DEV))
+    assert rel_err(yd, yr) <= TOL and rel_err(xd.grad, xr.grad) <= TOL
+    assert rel_err(mod.weight.grad, w.grad) <= TOL and rel_err(mod.bias.grad, b.grad) <= TOL
+    assert rel_err(mod.mean_scale.grad, ms.grad) <= TOL
+
+
+@pytest.mark.parametrize("ca,cb", [(16, 32), (64, 64), (12, 20), (3, 5)])
+def test_unpool_concat_writes_the_skip_concatenation_in_place(ca, cb):
+    """[skip || coarse[trace]] through the `ldo` column-slice form of the gather kernel: bit-identical to torch.cat of the
+    two halves, forward and backward."""
+    from stinet_b200 import ops
+    from stinet_b200.graph import ClusterCSR
+    g = torch.Generator().manual_seed(ca * 100 + cb)
+    n_f, n_c = 5000, 1300
+    trace = torch.randint(0, n_c, (n_f,), generator=g)
+    skip, xc = torch.randn(n_f, ca, generator=g), torch.randn(n_c, cb, generator=g)
+    go = torch.randn(n_f, ca + cb, generator=g)
+    sr, xr = skip.clone().requires_grad_(True), xc.clone().requires_grad_(True)
+    ref = torch.cat((sr, xr.index_select(0, trace)), -1)
+    ref.backward(go)
+    cl = ClusterCSR(trace.to(DEV), n_c)
+    sd, xd = skip.to(DEV).requires_grad_(True), xc.to(DEV).requires_grad_(True)
+    out = ops.unpool_concat(sd, xd, cl)
+    out.backward(go.to(DEV))
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(sd.grad.cpu(), sr.grad)
+    assert rel_err(xd.grad, xr.grad) <= TOL         # segmented sum in member order vs index_add order: same values up to rounding

@@ -142,8 +142,9 @@ def test_eval_no_grad_single_scene_matches_oracle():
 
 
 def test_full_size_properties_config2():
-    """BASELINE config 2 at full size (8 x 40,962-vertex icospheres, 4 trace-map levels, ngf 64): the oracle is too slow
-    here, so check size-independent properties: run-to-run bit determinism of outputs and gradients, batch independence
+    """BASELINE config 2 with the whole batch (8 x 40,962-vertex icospheres, 4 trace-map levels, ngf 64).  Values and
+    gradients at this size are checked against the oracle in test_gpu_baseline_configs.py (two crops of the batch); here
+    the size-independent properties of the full batch: run-to-run bit determinism of outputs and gradients, batch independence
     of the per-graph path (graph b of the batch == that graph alone, up to the whole-batch norm of the io blocks),
     output range, and finite gradients."""
     from stinet_b200 import synthetic

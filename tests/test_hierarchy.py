@@ -59,7 +59,6 @@ def test_product_function_matches_reference_golden_on_host_tensors(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="same code on CUDA tensors; not yet confirmed on hardware (round-1 GPU budget)")
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-3] for p in FIXTURES])
 def test_product_function_matches_reference_golden_on_device(path):
     _check_product(path, "cuda")

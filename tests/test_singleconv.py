@@ -70,6 +70,9 @@ def torch_stand_ins(monkeypatch):
     def unpool(xc, cl):
         return xc.index_select(0, cl.trace32.long())
 
+    def unpool_concat(skip, xc, cl):
+        return torch.cat((skip, xc.index_select(0, cl.trace32.long())), -1)
+
     def pool_mean(x, cl):
         return O.scatter_mean(x, cl.trace32.long(), cl.n_coarse)
 
@@ -83,6 +86,7 @@ def torch_stand_ins(monkeypatch):
     monkeypatch.setattr(graph, "build_csr", build_csr)
     monkeypatch.setattr(graph, "_require_cuda", lambda *a, **k: None)
     monkeypatch.setattr(ops, "unpool", unpool)
+    monkeypatch.setattr(ops, "unpool_concat", unpool_concat)
     monkeypatch.setattr(ops, "pool_mean", pool_mean)
     monkeypatch.setattr(ops, "pool_max", pool_max)
     monkeypatch.setattr(ops, "linear", linear)
