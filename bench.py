@@ -338,8 +338,16 @@ def main():
         return loss.item() if read_loss else loss
 
     graphed = None
-    if args.no_graph or infer:
+    if args.no_graph:
         step = eager_step
+    elif infer:
+        # full-scene inference through the public graphed-forward API: structure build + forward captured per batch shape
+        from stinet_b200.engine import GraphedForward
+        graphed = GraphedForward(net)
+
+        def step(b, read_loss=False):
+            out = graphed(b)
+            return float(out[0, 0].item()) if read_loss else out
     else:
         # the public whole-step API: the same work (structure build + fwd + loss + bwd + Adam) captured once per batch
         # shape into a CUDA graph and replayed; inputs are copied into the graph's static buffers on every call
@@ -391,9 +399,9 @@ def main():
     # ---- timed region 2: end to end through the public API from pinned host memory ----------------------------
     e2e = None
     if not args.no_e2e:
-        if graphed is None:
-            def e2e_step():
-                return step(host.to(dev, non_blocking=True), read_loss=True)
+        if graphed is None or infer:
+            def e2e_step():                                  # blocking H2D of the pinned batch, result element read back
+                return step(host.to(dev, non_blocking=True) if graphed is None else host, read_loss=True)
         else:
             # the loader pattern: the pinned batch of step k+1 is copied host->device on a copy stream while step k
             # runs (GraphedTrainStep.prefetch); every step still moves its own inputs H2D and reads its loss D2H
@@ -414,6 +422,7 @@ def main():
         e2e = {"value": world * n0 * K / (ms_e2e * 1e-3), "unit": "vertices/s",
                "h2d_bytes_per_step": host.tensor_bytes(), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
                "pipeline": "python launches, blocking H2D" if graphed is None else
+                           "H2D of the pinned batch into the graph's static inputs, graph replay, one output element read back" if infer else
                            "H2D of batch k+1 (pinned) overlaps step k on a copy stream; loss read back every step"}
 
     # ---- timed region 3 (extra key, not the headline): structure cached per sample ----------------
@@ -421,7 +430,7 @@ def main():
     # block-diagonal concatenation on the device, the host sends features only (no int64 COO tensors), and the captured
     # graph holds no structure-build kernels.  Same loader pattern and same H2D / D2H accounting as `e2e`.
     cached = None
-    if graphed is not None and not args.no_e2e and not args.no_cached:
+    if graphed is not None and not infer and not args.no_e2e and not args.no_cached:
         from stinet_b200.data import collate
         from stinet_b200.structure import SampleStructure
         samples = synthetic.make_samples(wl["kind"], wl["batch"], wl["net"]["n_levels"], seed=49 + 1000 * rank, **wl["gen"])
@@ -550,7 +559,9 @@ def main():
                                "graph-structure (CSR) build + forward + masked L1 + backward"
                                + (" + NCCL gradient all-reduce" if world > 1 else "") + " + Adam(amsgrad) step",
                        "dense_layers": precision,
-                       "launch": "python launches" if graphed is None else "whole-step CUDA graph replay (stinet_b200.engine)",
+                       "launch": "python launches" if graphed is None else
+                                 ("forward CUDA graph replay (stinet_b200.engine.GraphedForward)" if infer else
+                                  "whole-step CUDA graph replay (stinet_b200.engine)"),
                        "l2": "per-step working set (activations + weights, several GB) is far larger than the 126 MB L2; "
                              "no explicit flush"},
             "e2e": e2e, "e2e_cached_structure": cached, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,

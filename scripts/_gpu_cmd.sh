@@ -1,4 +1,12 @@
-timeout 600 python scripts/diag_singleconv.py fp32 > gpurun_out/diag_singleconv_r2_h.log 2>&1; echo "diag exit $?"; grep -E "^==|vs replay" gpurun_out/diag_singleconv_r2_h.log
-( timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > gpurun_out/pytest_r2_h.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_r2_h.log; grep -E "^(FAILED|ERROR)" gpurun_out/pytest_r2_h.log | head -30
-timeout 300 python bench.py --no-cached --kernels-out gpurun_out/kernels_r2_h.json > gpurun_out/bench_r2_h.json 2>gpurun_out/bench_r2_h.err; python -c "import json;b=json.load(open('gpurun_out/bench_r2_h.json'));print(b['ms_per_step'], b['cpu_baseline'], b['roofline']['kernel'], b['roofline']['achieved'], b['roofline']['frac'])"
-timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r2_h.json 2>gpurun_out/bench_ref_r2_h.err; cat gpurun_out/bench_ref_r2_h.json | head -c 700
+OUT=gpurun_out
+for W in cfg3 cfg1; do
+  timeout 400 python bench.py --workload $W --kernels-out $OUT/kernels_${W}_r2_i.json > $OUT/bench_${W}_r2_i.json 2> $OUT/bench_${W}_r2_i.err; echo "$W exit $?"
+  python -c "import json;b=json.load(open('$OUT/bench_${W}_r2_i.json'));print('$W', b['metric'], b['value'], b['ms_per_step'], b['e2e']['value'] if b.get('e2e') else None, b['cpu_baseline'])"
+done
+timeout 600 python bench.py --workload cfg3 --dtype f16 --no-cpu-baseline > $OUT/bench_cfg3_f16_r2_i.json 2> $OUT/bench_cfg3_f16_r2_i.err; python -c "import json;b=json.load(open('$OUT/bench_cfg3_f16_r2_i.json'));print('cfg3 f16', b['value'], b['ms_per_step'])"
+for D in fp32 f16; do
+  timeout 900 python bench.py --workload cfg5 --dtype $D --steps 5 --no-cached --kernels-out $OUT/kernels_cfg5_${D}_r2_i.json > $OUT/bench_cfg5_${D}_r2_i.json 2> $OUT/bench_cfg5_${D}_r2_i.err; echo "cfg5 $D exit $?"
+  python -c "import json;b=json.load(open('$OUT/bench_cfg5_${D}_r2_i.json'));print('cfg5 $D', b['value'], b['ms_per_step'], b['e2e']['value'] if b.get('e2e') else None, b['cpu_baseline'])"
+done
+timeout 300 python bench.py --workload cfg2 --dtype f16 --no-cpu-baseline --no-cached > $OUT/bench_cfg2_f16_r2_i.json 2> $OUT/bench_cfg2_f16_r2_i.err; python -c "import json;b=json.load(open('$OUT/bench_cfg2_f16_r2_i.json'));print('cfg2 f16', b['value'], b['ms_per_step'])"
+timeout 600 python bench.py --workload cfg1 --impl reference --steps 5 --warmup 2 > $OUT/bench_ref_cfg1_r2_i.json 2> $OUT/bench_ref_cfg1_r2_i.err; head -c 400 $OUT/bench_ref_cfg1_r2_i.json

@@ -209,3 +209,65 @@ class GraphedTrainStep:
                 self.reducer.overlap = overlap
             c.graph_b.replay()
         return c.loss
+
+
+class GraphedForward:
+    """Inference counterpart of GraphedTrainStep: structure build + forward (eval, no_grad) captured once per batch shape
+    signature into a CUDA graph and replayed -- full-scene inference is ~800 short kernels, launched one by one from
+    Python it is bound by launch overhead, not by the device.
+
+        fwd = GraphedForward(net.eval())
+        out = fwd(batch)            # H2D / D2D copies into the static inputs + one graph launch; `out` is the graph's
+                                    # static output buffer (clone it if it has to outlive the next call)
+    """
+
+    def __init__(self, net: torch.nn.Module, warmup: int = 1, max_cached: int = 8):
+        self.net, self.warmup, self.max_cached = net, max(int(warmup), 1), max_cached
+        self._cache: Dict[tuple, _Captured] = {}
+        self.captures = 0
+        self.replayed_launches = 0
+
+    def _run(self, static):
+        static.__dict__.pop("_stinet_cache", None)      # the structure is rebuilt from the batch's index tensors
+        with torch.no_grad():
+            return self.net(static)
+
+    def _capture(self, batch, sig) -> _Captured:
+        from . import ops
+        dev = next(self.net.parameters()).device
+        c = _Captured()
+        c.static = GraphBatch()
+        c.flat, c.views = _flat_views(list(_tensor_items(batch)), dev)
+        for k, v in c.views(c.flat).items():
+            v.copy_(batch[k], non_blocking=True)
+            c.static.__dict__[k] = v
+        c.static.__dict__["_nv_host"] = sig[1]
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):                 # eager warm-up: lazy inits, allocator, segment tables (no side effects)
+                self._run(c.static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        ops.invalidate_planes()
+        n0 = _abi.query("stinet_launch_count")
+        c.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(c.graph_a):
+            c.loss = self._run(c.static)                 # the static output
+        c.launches = _abi.query("stinet_launch_count") - n0
+        self.captures += 1
+        return c
+
+    def __call__(self, batch) -> torch.Tensor:
+        sig = batch_signature(batch)
+        c = self._cache.get(sig)
+        if c is None:
+            if len(self._cache) >= self.max_cached:
+                self._cache.pop(next(iter(self._cache)))
+            c = self._cache[sig] = self._capture(batch, sig)
+        for k, v in _tensor_items(batch):
+            c.static.__dict__[k].copy_(v, non_blocking=True)
+        c.graph_a.replay()
+        self.replayed_launches += c.launches
+        return c.loss
