@@ -332,7 +332,7 @@ def main():
             return float(out[0, 0].item()) if read_loss else out
         reducer.zero_grad()
         loss = masked_l1(net(b), b)
-        loss.backward()
+        (loss * reducer.loss_scale if world > 1 else loss).backward()
         reducer.finish()
         opt.step()
         return loss.item() if read_loss else loss

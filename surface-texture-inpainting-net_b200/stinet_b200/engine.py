@@ -15,12 +15,22 @@ every tensor shape plus the per-graph, per-level vertex counts `num_vertices` (t
 A batch with a new signature is captured on first use and cached; the reference's 2D trainer (equal-size image
 graphs) always hits one graph, the 3D trainer (variable crops) one graph per distinct crop topology.
 
-With more than one rank the gradient all-reduce runs between two graphs (forward+backward | optimizer), eagerly,
-on the same stream: the collective is a handful of launches and is not worth tying NCCL to graph capture.
+With more than one rank the bucketed gradient all-reduce is part of the SAME graph: NCCL collectives are capturable, the
+reducer's hooks issue each bucket's all-reduce on NCCL's stream as soon as backward has produced its last gradient, and
+the capture records that fork, so in a replayed step the transfers overlap the remaining backward kernels and the
+optimizer waits for them inside the graph (STINET_ALLREDUCE_IN_GRAPH=0 keeps the collectives outside, between a
+forward+backward graph and an optimizer graph).
+
+Capturing is free of side effects: the eager warm-up steps (lazy initialisation of kernels, allocator and optimizer
+state) run with the collectives switched off, and parameters, buffers and optimizer state are put back afterwards, so the
+first batch of a new shape is trained exactly once and every rank issues the same sequence of collectives whether it hit
+its graph cache or not.
 """
 from __future__ import annotations
 
 from typing import Callable, Dict, Optional
+
+import os
 
 import torch
 
@@ -50,7 +60,8 @@ def batch_signature(batch) -> tuple:
 
 
 class _Captured:
-    __slots__ = ("static", "graph_a", "graph_b", "loss", "launches", "flat", "views", "staging", "staged", "ready", "free")
+    __slots__ = ("static", "graph_a", "graph_b", "loss", "launches", "flat", "views", "staging", "staged", "ready", "free",
+                 "in_graph", "fresh")
 
 
 def _flat_views(items, device):
@@ -93,7 +104,10 @@ class GraphedTrainStep:
         else:
             self.net.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.net(static), static)
-        loss.backward()
+        if self.world > 1:
+            (loss * self.reducer.loss_scale).backward()  # mean over ranks = sum of the ranks' scaled gradients
+        else:
+            loss.backward()
         return loss
 
     def _finish(self):
@@ -113,19 +127,49 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        overlap = getattr(self.reducer, "overlap", False)
+        # ---- eager warm-up without side effects: lazy inits (kernel attributes, allocator, segment tables, optimizer
+        # state) happen here, then parameters / buffers / optimizer state are put back and no collective is issued
+        params = [p for p in self.net.parameters()]
+        buffers = [b for b in self.net.buffers()]
+        with torch.no_grad():
+            snap_p = [p.detach().clone() for p in params]
+            snap_b = [b.detach().clone() for b in buffers]
+            snap_o = {}
+            if self.opt is not None:
+                for p, st in self.opt.state.items():
+                    snap_o[p] = {k: v.detach().clone() for k, v in st.items() if torch.is_tensor(v)}
+        if self.reducer is not None:
+            self.reducer.enabled = False
         with torch.cuda.stream(side):
-            for _ in range(self.warmup):                 # eager warm-up: lazy inits, allocator, segment tables
+            for _ in range(self.warmup):
                 self._fwd_bwd(c.static)
-                self._finish()
                 if self.opt is not None:
                     self.opt.step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for p, v in zip(params, snap_p):
+                p.copy_(v)
+            for b, v in zip(buffers, snap_b):
+                b.copy_(v)
+            if self.opt is not None:
+                for p, st in self.opt.state.items():          # in place: the graph must see these very tensors
+                    old = snap_o.get(p)
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if old is not None and k in old:
+                                v.copy_(old[k])
+                            else:
+                                v.zero_()                     # state created by the warm-up: back to its initial zeros
         if self.reducer is not None:
-            self.reducer.overlap = False                 # hooks must not launch collectives inside the capture
+            self.reducer.enabled = True
+        torch.cuda.synchronize(dev)
         from . import ops
         ops.invalidate_planes()                          # the graph must contain the split of every operand it reads
+        in_graph = self.world > 1 and os.environ.get("STINET_ALLREDUCE_IN_GRAPH", "1") != "0"
+        overlap = getattr(self.reducer, "overlap", False)
+        if self.reducer is not None and not in_graph:
+            self.reducer.overlap = False                 # hooks must not launch collectives inside the capture
         n0 = _abi.query("stinet_launch_count")
         try:
             # with a process group alive, NCCL's watchdog thread polls CUDA events while we capture: only this thread's
@@ -134,16 +178,23 @@ class GraphedTrainStep:
             c.graph_a = torch.cuda.CUDAGraph()
             with torch.cuda.graph(c.graph_a, capture_error_mode=mode):
                 c.loss = self._fwd_bwd(c.static)
-                if self.world == 1 and self.opt is not None:
-                    self.opt.step()
+                if self.world == 1 or in_graph:
+                    self._finish()                       # waits for the bucket all-reduces the hooks forked off
+                    if self.opt is not None:
+                        self.opt.step()
             c.graph_b = None
-            if self.world > 1 and self.opt is not None:
+            c.fresh = None
+            if self.world > 1 and not in_graph:
+                c.fresh = {p: p.grad for p in self.reducer.params}     # static outputs of the backward graph
+                self.reducer.repoint()
+            if self.world > 1 and not in_graph and self.opt is not None:
                 c.graph_b = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(c.graph_b, pool=c.graph_a.pool(), capture_error_mode=mode):
                     self.opt.step()
         finally:
             if self.reducer is not None:
                 self.reducer.overlap = overlap
+        c.in_graph = in_graph
         c.launches = _abi.query("stinet_launch_count") - n0   # kernels of this library recorded into the graphs
         self.captures += 1
         return c
@@ -200,14 +251,11 @@ class GraphedTrainStep:
                 c.static.__dict__[k].copy_(v, non_blocking=True)
         c.graph_a.replay()
         self.replayed_launches += c.launches
-        if c.graph_b is not None:
-            overlap = self.reducer.overlap
-            self.reducer.overlap = False
-            try:
-                self.reducer.finish()
-            finally:
-                self.reducer.overlap = overlap
-            c.graph_b.replay()
+        if self.world > 1 and not getattr(c, "in_graph", False):
+            # collectives outside the graphs: the backward graph left fresh gradients behind; pack, reduce, then step
+            self.reducer.reduce_from(c.fresh)
+            if c.graph_b is not None:
+                c.graph_b.replay()
         return c.loss
 
 

@@ -2,11 +2,15 @@
 averaged with ONE collective family -- all-reduce over NCCL / NVLink 5 / NVSwitch.  The reference has
 no distributed code at all (its trainers assert a single GPU, trainers/inpainting3d_trainer.py:25).
 
-Gradients live in a few large flat fp32 buckets (parameters' .grad are views into them), so a bucket is reduced
-in place with a single all_reduce and no packing copies.  Buckets are filled in reverse registration order
-(decoder / output blocks first, which is the order backward produces them) and each all-reduce is launched from a
-post-accumulate-grad hook as soon as the bucket is complete, so the transfer overlaps the remaining backward
-kernels.  The mesh path itself has no data-path collective: graphs never span ranks.
+Gradients are reduced in a few large flat fp32 buckets filled in reverse registration order (decoder / output blocks
+first, which is the order backward produces them).  When the last gradient of a bucket has been produced, ONE
+multi-tensor copy moves the bucket's fresh gradient tensors into the flat buffer (no pre-zeroing, no accumulate pass),
+the parameters' .grad are re-pointed at the buffer's views, and the bucket's all-reduce is issued at once on NCCL's
+stream, so the transfer overlaps the remaining backward kernels; finish() only waits.  The same sequence is what
+GraphedTrainStep captures into its CUDA graph (NCCL collectives are graph-capturable), so a replayed step has the
+collectives forked off the backward kernels exactly as the eager step has.  The mean is taken by scaling the LOSS with
+1 / world (`loss_scale`) before backward, so the buckets need no extra pass after the sum.
+The mesh path itself has no data-path collective: graphs never span ranks.
 """
 from __future__ import annotations
 
@@ -36,73 +40,119 @@ def init_distributed(backend: Optional[str] = None):
 
 
 class GradAllReducer:
-    """Bucketed, overlapped gradient averaging for a replicated module."""
+    """Bucketed, overlapped gradient averaging for a replicated module.
 
-    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 64 << 20, overlap: bool = True):
+        reducer = GradAllReducer(net)
+        reducer.zero_grad()
+        (loss_fn(net(batch)) * reducer.loss_scale).backward()     # hooks issue the all-reduces bucket by bucket
+        reducer.finish()                                          # waits; p.grad now holds the mean over ranks
+        optimizer.step()
+    """
+
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 32 << 20, overlap: bool = True):
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.loss_scale = 1.0 / self.world
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.overlap = overlap and self.world > 1
+        self.enabled = True                         # False: hooks and finish() do nothing (side-effect-free warm-up)
         self.buckets: List[torch.Tensor] = []
+        self._groups: List[list] = []
+        self._views: List[list] = []
         self._bucket_of = {}
         self._pending: List[int] = []
+        self._issued: List[bool] = []
         self._handles = []
         if self.world == 1:
-            # nothing to reduce: leave .grad unset so autograd hands each weight gradient over without the
-            # zero-fill + accumulate pass that pre-allocated bucket views cost (two launches per parameter)
-            self._sizes = []
             return
         # reverse order: the last layers' gradients are produced first
         cur, cur_bytes = [], 0
-        groups = []
         for p in reversed(self.params):
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= bucket_bytes:
-                groups.append(cur)
+                self._groups.append(cur)
                 cur, cur_bytes = [], 0
         if cur:
-            groups.append(cur)
-        for b, group in enumerate(groups):
+            self._groups.append(cur)
+        for b, group in enumerate(self._groups):
             flat = torch.zeros(sum(p.numel() for p in group), dtype=torch.float32, device=group[0].device)
-            off = 0
+            views, off = [], 0
             for p in group:
-                p.grad = flat[off:off + p.numel()].view_as(p)       # autograd accumulates in place into the view
+                views.append(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
                 self._bucket_of[p] = b
             self.buckets.append(flat)
-            self._pending.append(len(group))
-        self._sizes = list(self._pending)
-        if self.world > 1:
-            for p in self.params:
-                p.register_post_accumulate_grad_hook(self._on_grad)
+            self._views.append(views)
+        self._sizes = [len(g) for g in self._groups]
+        self._pending = list(self._sizes)
+        self._issued = [False] * len(self._groups)
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._on_grad)
 
     def zero_grad(self):
-        if self.world == 1:
-            for p in self.params:
-                p.grad = None
-            return
-        for flat in self.buckets:
-            flat.zero_()
-        self._pending = list(self._sizes)
-        self._handles = []
+        """Gradients are handed over by autograd as fresh tensors (no zero-fill, no accumulate pass)."""
+        for p in self.params:
+            p.grad = None
+        if self.world > 1:
+            self._pending = list(self._sizes)
+            self._issued = [False] * len(self._groups)
+            self._handles = []
+
+    def _issue(self, b: int):
+        """Pack bucket b (one multi-tensor copy; a parameter without a gradient contributes zeros), re-point the .grad of
+        its parameters at the flat buffer and start the all-reduce."""
+        group, views = self._groups[b], self._views[b]
+        have = [(v, p.grad) for v, p in zip(views, group) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        for v, p in zip(views, group):
+            if p.grad is None:
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v, p in zip(views, group):
+            p.grad = v
+        self._issued[b] = True
+        self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, async_op=True))
 
     def _on_grad(self, p):
-        if not self.overlap:                       # e.g. while a step is being captured into a CUDA graph
+        if not (self.enabled and self.overlap):
             return
         b = self._bucket_of[p]
         self._pending[b] -= 1
-        if self._pending[b] == 0:
-            self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, async_op=True))
+        if self._pending[b] == 0 and not self._issued[b]:
+            self._issue(b)
 
     def finish(self):
-        """Call after backward(): waits for (or issues) the all-reduces and turns sums into means."""
-        if self.world == 1:
+        """Call after backward(): issues the all-reduce of every bucket the hooks have not started (overlap off, or a
+        parameter that received no gradient this step) and waits for all of them."""
+        if self.world == 1 or not self.enabled:
             return
-        if not self.overlap:
-            self._handles = [dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=True) for f in self.buckets]
+        for b in range(len(self._groups)):
+            if not self._issued[b]:
+                self._issue(b)
         for h in self._handles:
             h.wait()
-        inv = 1.0 / self.world
-        for flat in self.buckets:
-            flat.mul_(inv)
         self._handles = []
+
+    # ---- collectives outside a captured graph (GraphedTrainStep with STINET_ALLREDUCE_IN_GRAPH=0) ------------------
+    def repoint(self):
+        """Point every .grad at its bucket view without packing or reducing (what a captured optimizer step must read)."""
+        for views, group in zip(self._views, self._groups):
+            for v, p in zip(views, group):
+                p.grad = v
+
+    def reduce_from(self, fresh: dict):
+        """Pack the given gradient tensors (parameter -> tensor, e.g. the static outputs of a backward graph) into the
+        buckets and all-reduce them; returns when the reduced means are in the bucket views."""
+        if self.world == 1:
+            return
+        handles = []
+        for b, (views, group) in enumerate(zip(self._views, self._groups)):
+            have = [(v, fresh[p]) for v, p in zip(views, group) if fresh.get(p) is not None]
+            for v, p in zip(views, group):
+                if fresh.get(p) is None:
+                    v.zero_()
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+            handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, async_op=True))
+        for h in handles:
+            h.wait()

@@ -33,9 +33,23 @@ def _worker(rank, world, port, overlap, out):
     x = torch.randn(32, 6, generator=g)
     for _ in range(2):                                      # second iteration checks zero_grad / hook re-arming
         red.zero_grad()
-        net(x).square().mean().backward()
+        (net(x).square().mean() * red.loss_scale).backward()
         red.finish()
+    assert all(p.grad.data_ptr() == v.data_ptr() for g_, vs in zip(red._groups, red._views) for p, v in zip(g_, vs))
     flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    # a parameter that receives no gradient must not keep its bucket from being reduced (it contributes zeros), and a
+    # disabled reducer (warm-up of a graph capture) must leave gradients and collectives alone
+    red.zero_grad()
+    (net[0](x).square().mean() * red.loss_scale).backward()      # only the first Linear gets gradients
+    red.finish()
+    assert all(p.grad is not None for p in net.parameters())
+    assert float(net[4].weight.grad.abs().max()) == 0.0 and float(net[0].weight.grad.abs().max()) > 0.0
+    red.enabled = False
+    red.zero_grad()
+    net(x).square().mean().backward()
+    red.finish()
+    assert all(p.grad.data_ptr() != v.data_ptr() for g_, vs in zip(red._groups, red._views) for p, v in zip(g_, vs))
+    red.enabled = True
     if rank == 0:
         torch.save(flat, out)
     dist.barrier()
