@@ -68,27 +68,21 @@ __global__ void __launch_bounds__(kScanThreads) scan_chunk_sums(const int32_t* _
   if (threadIdx.x == 0) chunk_sum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_chunk_offsets(int32_t* __restrict__ chunk_sum, int n_chunks) {
-  __shared__ int carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n_chunks; base += kScanThreads) {
-    int i = base + threadIdx.x;
-    int v = i < n_chunks ? chunk_sum[i] : 0;
+// rowptr[i] = sum_{k<i} cnt[k] for i in [0, n_rows]  (n = n_rows + 1 outputs; cnt[n_rows] is read as 0)
+// (the exclusive offset of a chunk = sum of the chunk sums before it, added up by the CTA itself in a fixed order: a few
+// hundred values at most, so no separate offsets kernel)
+__global__ void __launch_bounds__(kScanThreads) scan_write(const int32_t* __restrict__ cnt, int64_t n_rows,
+                                                           const int32_t* __restrict__ chunk_sum,
+                                                           int32_t* __restrict__ rowptr) {
+  __shared__ int chunk_off_s;
+  {
+    int part = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += kScanThreads) part += chunk_sum[c];
     int total;
-    int inc = block_incl_scan(v, &total);
-    int carry = carry_s;
-    if (i < n_chunks) chunk_sum[i] = carry + inc - v;  // exclusive
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + total;
+    block_incl_scan(part, &total);
+    if (threadIdx.x == 0) chunk_off_s = total;
     __syncthreads();
   }
-}
-
-// rowptr[i] = sum_{k<i} cnt[k] for i in [0, n_rows]  (n = n_rows + 1 outputs; cnt[n_rows] is read as 0)
-__global__ void __launch_bounds__(kScanThreads) scan_write(const int32_t* __restrict__ cnt, int64_t n_rows,
-                                                           const int32_t* __restrict__ chunk_off,
-                                                           int32_t* __restrict__ rowptr) {
   int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
   int v[kScanItems];
   int s = 0;
@@ -99,7 +93,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_write(const int32_t* __rest
   }
   int total;
   int inc = block_incl_scan(s, &total);
-  int run = chunk_off[blockIdx.x] + inc - s;
+  int run = chunk_off_s + inc - s;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     if (base + k <= n_rows) rowptr[base + k] = run;
@@ -144,7 +138,7 @@ __global__ void csr_sort_small_rows(const int32_t* __restrict__ rowptr, int64_t 
 }
 
 // rank sort of long rows (positions are distinct, so ranks are a permutation): tmp[beg + rank] = value
-__global__ void csr_rank_big_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+__global__ void csr_rank_big_rows(const int32_t* __restrict__ rowptr, int32_t* __restrict__ perm,
                                   const int32_t* __restrict__ big_rows, const int32_t* __restrict__ n_big,
                                   int32_t* __restrict__ tmp) {
   const int nb = *n_big;
@@ -157,23 +151,26 @@ __global__ void csr_rank_big_rows(const int32_t* __restrict__ rowptr, const int3
       for (int b = beg; b < end; ++b) rank += (perm[b] < v);
       tmp[beg + rank] = v;
     }
-  }
-}
-__global__ void csr_copy_big_rows(const int32_t* __restrict__ rowptr, int32_t* __restrict__ perm,
-                                  const int32_t* __restrict__ big_rows, const int32_t* __restrict__ n_big,
-                                  const int32_t* __restrict__ tmp) {
-  const int nb = *n_big;
-  for (int q = blockIdx.x; q < nb; q += gridDim.x) {
-    int r = big_rows[q];
-    int beg = rowptr[r], end = rowptr[r + 1];
+    __syncthreads();                                   // the row is owned by this CTA: ranks done, copy back
     for (int a = beg + threadIdx.x; a < end; a += blockDim.x) perm[a] = tmp[a];
+    __syncthreads();
   }
 }
-
-__global__ void csr_gather_col(const int64_t* __restrict__ other, const int32_t* __restrict__ perm, int64_t n_items,
-                               int64_t n_rows, int32_t* __restrict__ col, int32_t* __restrict__ status) {
+// Out-of-range keys are dropped by count / fill (status bit 0), so only the first rowptr[n_rows] entries of perm are
+// written: the tail is filled here (perm = -1, col = 0; every later pass over perm skips negative entries) instead of being
+// left to chance.
+__global__ void csr_gather_col(const int64_t* __restrict__ other, int32_t* __restrict__ perm, int64_t n_items,
+                               int64_t n_rows, const int32_t* __restrict__ rowptr, int32_t* __restrict__ col,
+                               int32_t* __restrict__ status) {
+  const int64_t n_valid = rowptr[n_rows];
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_items;
        k += (int64_t)gridDim.x * blockDim.x) {
+    if (k >= n_valid) {
+      perm[k] = -1;
+      if (col) col[k] = 0;
+      continue;
+    }
+    if (!col) continue;
     int64_t v = other[perm[k]];
     bool ok = (v >= 0) & (v < n_rows);
     col[k] = ok ? (int32_t)v : 0;
@@ -184,13 +181,17 @@ __global__ void csr_gather_col(const int64_t* __restrict__ other, const int32_t*
 // tpos_s[k_s] = position, in the by-target CSR, of the edge that sits at position k_s of the by-source CSR
 // (both are permutations of the same original edge ids): inv[eid_t[k]] = k, then tpos_s[k_s] = inv[eid_s[k_s]].
 __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    inv[perm[k]] = (int32_t)k;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t e = perm[k];
+    if (e >= 0 && e < n) inv[e] = (int32_t)k;          // the tail left by out-of-range keys is marked -1
+  }
 }
 __global__ void gather_i32_kernel(const int32_t* __restrict__ table, const int32_t* __restrict__ idx, int64_t n,
                                   int32_t* __restrict__ out) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    out[k] = table[idx[k]];
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t i = idx[k];
+    out[k] = i >= 0 ? table[i] : 0;
+  }
 }
 
 // Block-diagonal batching of per-sample structures: part p of the destination is src[p][0..len) + add[p].
@@ -276,15 +277,14 @@ extern "C" int stinet_csr_build(const int64_t* key, const int64_t* other, int64_
     K(csr_count_kernel<<<grid_items, threads, 0, stream>>>(key, n_items, n_rows, w.cnt, key32, status));
   const int n_chunks = (int)ceil_div(n_rows + 1, kScanChunk);
   K(scan_chunk_sums<<<n_chunks, kScanThreads, 0, stream>>>(w.cnt, n_rows, w.chunk));
-  K(scan_chunk_offsets<<<1, kScanThreads, 0, stream>>>(w.chunk, n_chunks));
   K(scan_write<<<n_chunks, kScanThreads, 0, stream>>>(w.cnt, n_rows, w.chunk, rowptr));
   if (n_items > 0) {
     K(csr_fill_kernel<<<grid_items, threads, 0, stream>>>(key, n_items, n_rows, rowptr, w.cursor, perm));
     K(csr_sort_small_rows<<<wave_grid(n_rows, threads, 8), threads, 0, stream>>>(rowptr, n_rows, perm, w.big_rows,
                                                                                  w.n_big));
     K(csr_rank_big_rows<<<kSMs * 2, 256, 0, stream>>>(rowptr, perm, w.big_rows, w.n_big, w.tmp));
-    K(csr_copy_big_rows<<<kSMs * 2, 256, 0, stream>>>(rowptr, perm, w.big_rows, w.n_big, w.tmp));
-    if (other) K(csr_gather_col<<<grid_items, threads, 0, stream>>>(other, perm, n_items, n_rows, col, status));
+    // (with `other` == NULL the kernel only has a tail to fill; meshes have none, but the launch decides that on the device)
+    K(csr_gather_col<<<grid_items, threads, 0, stream>>>(other, perm, n_items, n_rows, rowptr, other ? col : nullptr, status));
   }
   return check_launch("csr_build");
 }

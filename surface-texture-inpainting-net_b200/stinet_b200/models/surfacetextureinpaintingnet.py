@@ -222,7 +222,13 @@ class SurfaceTextureInpaintingNet(nn.Module):
                 key = f"hierarchy_dil_{d}_edge_index_{L}"
             else:
                 key = f"hierarchy_edge_index_{L}" if L > 0 else 'edge_index'
-            out = block(out, cache.edges(key, L), seg(L))
+            edges = cache.edges(key, L)
+            if d > 1 and cache.batch_size > 1 and not torch.cuda.is_current_stream_capturing():
+                # PyG's default __inc__ offsets the dilated keys of a Batch by the LEVEL-0 vertex count (utils/data_utils.py
+                # :23-42 only special-cases the hierarchy_* keys), i.e. out of range at level L for B > 1; the reference
+                # dies with an index error there (it only uses B = 1 with dilations).  Same here, loudly (one host read).
+                cache.check_status()
+            out = block(out, edges, seg(L))
 
         for i, block in enumerate(self.decoder_blocks):
             level = i + 1

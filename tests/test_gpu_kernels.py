@@ -61,6 +61,32 @@ def test_csr_flags_out_of_range_index():
     assert int(status.item()) == 1
 
 
+def test_csr_out_of_range_items_are_dropped_not_dereferenced():
+    """Keys outside [0, n) are counted out (status bit 0) and leave a tail in perm that every later pass must skip: the
+    by-target / by-source structures and the cross positions of the VALID items equal the oracle's on the filtered edge
+    list, and nothing reads or writes through a garbage index (the reference would raise an index error instead)."""
+    from stinet_b200.graph import EdgeCSR
+    g = torch.Generator().manual_seed(3)
+    n, e = 500, 6000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    bad = torch.randperm(e, generator=g)[:300]
+    ei[1, bad[:150]] = n + torch.randint(0, 1000, (150,), generator=g)       # targets beyond the level
+    ei[1, bad[150:]] = -1 - torch.randint(0, 5, (150,), generator=g)         # negative targets
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    csr = EdgeCSR(ei.to(DEV), n, status)
+    tpos = csr.tpos_s()
+    torch.cuda.synchronize()
+    assert int(status.item()) == 1
+    ok = (ei[1] >= 0) & (ei[1] < n)
+    n_valid = int(ok.sum())
+    rp, perm = O.csr_by_key(ei[1][ok], n)
+    orig = torch.nonzero(ok).flatten()[perm.long()].to(torch.int32)           # original positions of the valid items
+    assert torch.equal(csr.rowptr_t.cpu(), rp) and int(csr.rowptr_t[-1]) == n_valid
+    assert torch.equal(csr.eid_t.cpu()[:n_valid], orig)
+    assert bool((csr.eid_t.cpu()[n_valid:] == -1).all()) and bool((csr.col_t.cpu()[n_valid:] == 0).all())
+    assert bool((tpos.cpu() >= 0).all()) and bool((tpos.cpu() < e).all())
+
+
 @pytest.mark.parametrize("kind", ["ico", "graph18_isolated", "dilated_asym", "multi_edges"])
 @pytest.mark.parametrize("reduce", ["mean", "add", "max"])
 @pytest.mark.parametrize("c", [3, 16, 128])
