@@ -314,6 +314,42 @@ int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* 
  * kernel that produces dP (per-CTA partials in `workspace`, fixed-order second stage). */
 size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden);
 
+/* ---- integer sort primitives and hierarchy construction (replace the Python loops and np.unique calls
+ * of preprocessing/graph_level_generation.py:194-244 `vertex_clustering`).  All results are bit-identical to the reference's:
+ * integers by construction, coordinates because members are summed sequentially in ascending vertex id in the input dtype.
+ *   sort_pairs_u64      stable LSD radix sort (8 bits per pass, ceil(key_bits / 8) passes) of (key, value) pairs; vals_in NULL
+ *                       = the positions 0..n-1 (argsort), vals_out NULL = keys only.  keys_in is not modified.
+ *   csr_degree_order    order[k] = k-th row of a CSR by DESCENDING degree, ties by ascending row (north_star's degree sort)
+ *   voxel_bins          bins[i,a] = floor_divide(coords[i,a], voxel) with numpy's float semantics (:207); minmax[0..2] =
+ *                       per-axis minimum, [3..5] = maximum (int64)
+ *   voxel_keys          keys[i] = lexicographic rank key of bin i inside the bounding box (the row order of np.unique(axis=0))
+ *   unique_sorted_u64   ids[i] = index of key i among the distinct keys < limit (keys >= limit are ignored), count[0] = number
+ *                       of distinct keys < limit      (:208-209 return_inverse, after the sort)
+ *   cluster_finish      trace[idx_sorted[i]] = ids[i];  start[c] = first sorted position of cluster c, start[n_coarse] = n
+ *   cluster_centroids   out[c] = float32(mean of coords[members of c]) (:238-242)
+ *   coarse_edge_keys    key[e] = trace[src] * n_coarse + trace[dst], self loops (and out-of-range ends: status bit 0) = n_coarse^2
+ *   coarse_edges_emit   the distinct keys < n_coarse^2 as the [2, n_out] coarse edge set sorted by (vertex, neighbour) (:215-228) */
+size_t stinet_sort_workspace_bytes(int64_t n);
+int stinet_sort_pairs_u64(const uint64_t* keys_in, const int32_t* vals_in, uint64_t* keys_out, int32_t* vals_out, int64_t n,
+                          int key_bits, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+size_t stinet_csr_degree_order_workspace_bytes(int64_t n_rows);
+int stinet_csr_degree_order(const int32_t* rowptr, int64_t n_rows, int32_t* order, void* workspace, size_t workspace_bytes,
+                            stinet_stream_t stream);
+int stinet_voxel_bins(const void* coords, int is_f64, int64_t n, double voxel, int64_t* bins, int64_t* minmax,
+                      stinet_stream_t stream);
+int stinet_voxel_keys(const int64_t* bins, const int64_t* minmax, int64_t n, uint64_t* keys, stinet_stream_t stream);
+size_t stinet_unique_workspace_bytes(int64_t n);
+int stinet_unique_sorted_u64(const uint64_t* keys_sorted, int64_t n, uint64_t limit, int32_t* ids, int32_t* count,
+                             void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+int stinet_cluster_finish(const int32_t* idx_sorted, const int32_t* ids, int64_t n, int64_t n_coarse, int64_t* trace,
+                          int32_t* start, stinet_stream_t stream);
+int stinet_cluster_centroids(const void* coords, int is_f64, const int32_t* idx_sorted, const int32_t* start,
+                             int64_t n_coarse, float* out, stinet_stream_t stream);
+int stinet_coarse_edge_keys(const int64_t* src, const int64_t* dst, int64_t n_edges, const int64_t* trace, int64_t n_fine,
+                            int64_t n_coarse, uint64_t* keys, int32_t* status, stinet_stream_t stream);
+int stinet_coarse_edges_emit(const uint64_t* keys_sorted, const int32_t* ids, int64_t n_edges, int64_t n_coarse, int64_t n_out,
+                             int64_t* out, stinet_stream_t stream);
+
 /* ---- per-step graph metrics (replace utils/metrics/graph_metrics.py:6-72 as called from
  * trainers/inpainting3d_trainer.py:254-263) on the level-0 CSR by target.  Scalar results are written to `out` on the
  * device (float[1], psnr float[2] = {score, rows used}); reductions are deterministic (double partials, fixed order).

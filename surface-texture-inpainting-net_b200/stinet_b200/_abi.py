@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("STINET_B200_LIB") or os.path.join(_HERE, "libstinet_b200.so")   # override: debug builds only
 
 P, I64, I, F, SZ = c_void_p, c_int64, c_int, c_float, c_size_t
+D, U64 = ctypes.c_double, ctypes.c_uint64
 
 # name -> (restype, argtypes); mirrors include/stinet_b200.h one to one
 SIGNATURES = {
@@ -51,6 +52,18 @@ SIGNATURES = {
     "stinet_affnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, P, P, P, I64, P]),
     "stinet_affnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I, P, P, P, P, P, I64, P, P, P, P, SZ, P]),
     "stinet_bn_running_update": (I, [P, P, I64, F, F, I64, P, P, P]),
+    "stinet_sort_workspace_bytes": (SZ, [I64]),
+    "stinet_sort_pairs_u64": (I, [P, P, P, P, I64, I, P, SZ, P]),
+    "stinet_csr_degree_order_workspace_bytes": (SZ, [I64]),
+    "stinet_csr_degree_order": (I, [P, I64, P, P, SZ, P]),
+    "stinet_voxel_bins": (I, [P, I, I64, D, P, P, P]),
+    "stinet_voxel_keys": (I, [P, P, I64, P, P]),
+    "stinet_unique_workspace_bytes": (SZ, [I64]),
+    "stinet_unique_sorted_u64": (I, [P, I64, U64, P, P, P, SZ, P]),
+    "stinet_cluster_finish": (I, [P, P, I64, I64, P, P, P]),
+    "stinet_cluster_centroids": (I, [P, I, P, P, I64, P, P]),
+    "stinet_coarse_edge_keys": (I, [P, P, I64, P, I64, I64, P, P, P]),
+    "stinet_coarse_edges_emit": (I, [P, P, I64, I64, I64, P, P]),
     "stinet_metrics_workspace_bytes": (SZ, [I64]),
     "stinet_graph_laplace": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_graph_laplace_variance": (I, [P, I64, P, P, I64, P, P, SZ, P]),

@@ -105,6 +105,19 @@ class EdgeCSR:
             self._by_source = (rowptr_s, col_s, eid_s)
         return self._by_source
 
+    def degree_order(self) -> torch.Tensor:
+        """int32 [n]: the rows by DESCENDING in-degree, ties in ascending row order (stinet_csr_degree_order).  A row
+        schedule for kernels that map several rows onto one warp; the warp-per-row message kernels of this package keep
+        the natural order, which preserves the gather locality of neighbouring mesh vertices."""
+        if getattr(self, "_degree_order", None) is None:
+            out = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.rowptr_t.device)
+            nb = _abi.query("stinet_csr_degree_order_workspace_bytes", self.n)
+            ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=out.device)
+            _abi.call("stinet_csr_degree_order", self.rowptr_t.data_ptr(), self.n, out.data_ptr(), ws.data_ptr(), nb, _stream(),
+                      cost=(self.n * 60, 0, ""))
+            self._degree_order = out[:self.n]
+        return self._degree_order
+
     def dq_factor(self) -> torch.Tensor:
         """Device float: max_j sum_{j->i} 1/deg_i -- |dQ| <= max|dhid| * dq_factor in the message-stage backward (the
         bound its fp16 output planes are scaled with)."""
