@@ -42,7 +42,7 @@ def test_graphed_step_equals_eager_step(prefetch):
             step = GraphedTrainStep(net, _loss, opt, warmup=1)
             pinned = [b.pin_memory() for b in batches]
             if prefetch:                                  # loader pattern: batch k+1 moves H2D while step k runs
-                assert step.prefetch(pinned[0])
+                assert not step.prefetch(pinned[0])       # (nothing to stage into before the shape has been captured)
             for i, b in enumerate(pinned):
                 loss = step(b)
                 if prefetch and i + 1 < len(pinned):
