@@ -568,7 +568,17 @@ def main():
             "kernels": kernels,
         })
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: the step graphs hold captured NCCL kernels, and destroy_process_group() with
+        # such graphs alive can block for minutes (observed on 2 x B200).  Everything is measured and printed by now; all
+        # ranks meet at a barrier, flush, and exit with status 0.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if _RESULT_OUT is not None:
+            _RESULT_OUT.flush()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
