@@ -115,10 +115,10 @@ def path_roofline(summ: dict, steps: int, hbm_gbs: float, bf16_tflops: float, pa
 
 
 def masked_l1(out, b):
-    """trainer glue that stays PyTorch: reference trainers/inpainting3d_trainer.py:127-137"""
-    composed = torch.where((b.mask > 0).expand_as(b.color), out, b.color)
-    loss = (composed - b.color).abs() * torch.pow(0.99, b.mask.squeeze().float()).unsqueeze(1)
-    return loss.mean()
+    """the trainer's loss, reference trainers/inpainting3d_trainer.py:127-137 (torch.where + L1 + 0.99^mask + mean), as the
+    package's fused op (one forward and one backward kernel; tests/test_gpu_kernels.py checks it against the torch chain)"""
+    from stinet_b200 import ops
+    return ops.masked_l1_loss(out, b.color, b.mask)
 
 
 class ClockSampler:

@@ -314,6 +314,25 @@ int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* 
  * kernel that produces dP (per-CTA partials in `workspace`, fixed-order second stage). */
 size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden);
 
+/* ---- the tail of the network and the trainer's loss
+ *   head        out[N,3] = tanh(h[N,C] W^T + b), W [3,C] -- reference models/surfacetextureinpaintingnet.py:466-469
+ *               (final_linear2 + Tanh); the 3-wide Linear is evaluated in registers (C in {8,...,256}, a power of two).
+ *               bwd: dh = (dout (1 - out^2)) W, dW, db (two-stage sums; dh nullable).
+ *   masked_l1   loss[0] = mean over N x channels of |where(mask > 0, out, color) - color| * 0.99^mask, mask [N] float
+ *               -- trainers/inpainting3d_trainer.py:127-137 (torch.where + L1Loss(reduction='none') + pow + mean);
+ *               bwd: dout = gloss[0] * [mask > 0] * 0.99^mask * sign(out - color) / (N channels). */
+size_t stinet_head_workspace_bytes(int64_t n_rows, int64_t channels);
+int stinet_head_fwd(const float* h, int64_t ldh, const float* W, const float* b, int64_t n_rows, int64_t channels, float* out,
+                    stinet_stream_t stream);
+int stinet_head_bwd(const float* h, int64_t ldh, const float* W, const float* out, const float* dout, int64_t n_rows,
+                    int64_t channels, float* dh, int64_t lddh, float* dW, float* db, void* workspace, size_t workspace_bytes,
+                    stinet_stream_t stream);
+size_t stinet_masked_l1_workspace_bytes(int64_t n_rows);
+int stinet_masked_l1_fwd(const float* out, const float* color, const float* mask, int64_t n_rows, int64_t channels,
+                         float* loss, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+int stinet_masked_l1_bwd(const float* out, const float* color, const float* mask, const float* gloss, int64_t n_rows,
+                         int64_t channels, float* dout, stinet_stream_t stream);
+
 /* ---- integer sort primitives and hierarchy construction (replace the Python loops and np.unique calls
  * of preprocessing/graph_level_generation.py:194-244 `vertex_clustering`).  All results are bit-identical to the reference's:
  * integers by construction, coordinates because members are summed sequentially in ascending vertex id in the input dtype.

@@ -52,6 +52,12 @@ SIGNATURES = {
     "stinet_affnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, P, P, P, I64, P]),
     "stinet_affnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I, P, P, P, P, P, I64, P, P, P, P, SZ, P]),
     "stinet_bn_running_update": (I, [P, P, I64, F, F, I64, P, P, P]),
+    "stinet_head_workspace_bytes": (SZ, [I64, I64]),
+    "stinet_head_fwd": (I, [P, I64, P, P, I64, I64, P, P]),
+    "stinet_head_bwd": (I, [P, I64, P, P, P, I64, I64, P, I64, P, P, P, SZ, P]),
+    "stinet_masked_l1_workspace_bytes": (SZ, [I64]),
+    "stinet_masked_l1_fwd": (I, [P, P, P, I64, I64, P, P, SZ, P]),
+    "stinet_masked_l1_bwd": (I, [P, P, P, P, I64, I64, P, P]),
     "stinet_sort_workspace_bytes": (SZ, [I64]),
     "stinet_sort_pairs_u64": (I, [P, P, P, P, I64, I, P, SZ, P]),
     "stinet_csr_degree_order_workspace_bytes": (SZ, [I64]),

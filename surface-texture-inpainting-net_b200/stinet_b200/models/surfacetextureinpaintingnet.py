@@ -249,6 +249,9 @@ class SurfaceTextureInpaintingNet(nn.Module):
             out = ops.norm_act_res(out, None, None, False, ACT_ELU)
         else:
             out = nn.functional.elu(self.final_norm1(out, final_seg))
+        fused = ops.head_tanh(out, self.final_linear2.weight, self.final_linear2.bias)   # Linear(ngf, 3) + Tanh in one kernel
+        if fused is not None:
+            return fused
         out = ops.linear(out, self.final_linear2.weight, self.final_linear2.bias, None, prec)
         return torch.tanh(out)
 

@@ -910,3 +910,84 @@ class BatchNorm1d(torch.nn.BatchNorm1d):
             self.num_batches_tracked.add_(updates)
         return batch_norm(input, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
                           self.running_var if self.track_running_stats else None, training, self.momentum, self.eps, updates)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# network tail and trainer loss
+
+
+class HeadTanhFn(Function):
+    """out = tanh(h W^T + b) for the 3-channel output head (final_linear2 + Tanh): one kernel, the Linear in registers."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias):
+        h, weight = _mat(h), weight.contiguous()
+        n, c = h.shape
+        out = torch.empty((n, 3), dtype=torch.float32, device=h.device)
+        _abi.call("stinet_head_fwd", h.data_ptr(), _ld(h), weight.data_ptr(), _ptr(bias), n, c, out.data_ptr(), _stream(),
+                  cost=(4 * n * (c + 3), 6 * n * c, f"C{c}"))
+        ctx.save_for_backward(h, weight, out)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        h, weight, out = ctx.saved_tensors
+        n, c = h.shape
+        dev = h.device
+        dout = dout.contiguous()
+        dh = torch.empty((n, c), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty((3, c), dtype=torch.float32, device=dev)
+        db = torch.empty((3,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+        nb = _abi.query("stinet_head_workspace_bytes", n, c)
+        ws = _ws(nb, dev)
+        _abi.call("stinet_head_bwd", h.data_ptr(), _ld(h), weight.data_ptr(), out.data_ptr(), dout.data_ptr(), n, c, _ptr(dh), c,
+                  dw.data_ptr(), _ptr(db), ws.data_ptr(), nb, _stream(), cost=(4 * n * (2 * c + 6), 12 * n * c, f"C{c}"))
+        return dh, dw, db
+
+
+def head_tanh(h, weight, bias):
+    """The fused head when the shapes allow it (3 outputs, C a power of two in 8..256, aligned rows), else None."""
+    c = h.shape[1]
+    if weight.shape[0] != 3 or c not in (8, 16, 32, 64, 128, 256) or not h.is_cuda:
+        return None
+    h = _mat(h)
+    if _ld(h) % 4 or h.data_ptr() % 16:
+        return None
+    return HeadTanhFn.apply(h, weight, bias)
+
+
+class MaskedL1Fn(Function):
+    """loss = mean(|where(mask > 0, out, color) - color| * 0.99^mask)  (trainers/inpainting3d_trainer.py:127-137)."""
+
+    @staticmethod
+    def forward(ctx, out, color, mask):
+        out, color = out.contiguous(), color.contiguous()
+        n, c = out.shape
+        m = mask.reshape(-1).to(torch.float32).contiguous()
+        assert color.shape == out.shape and m.numel() == n
+        loss = torch.empty((), dtype=torch.float32, device=out.device)
+        nb = _abi.query("stinet_masked_l1_workspace_bytes", n)
+        ws = _ws(nb, out.device)
+        _abi.call("stinet_masked_l1_fwd", out.data_ptr(), color.data_ptr(), m.data_ptr(), n, c, loss.data_ptr(), ws.data_ptr(), nb,
+                  _stream(), cost=(4 * n * (2 * c + 1), 4 * n * c, ""))
+        ctx.save_for_backward(out, color, m)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        out, color, m = ctx.saved_tensors
+        n, c = out.shape
+        g = g.reshape(1).to(torch.float32).contiguous()
+        dout = torch.empty_like(out)
+        _abi.call("stinet_masked_l1_bwd", out.data_ptr(), color.data_ptr(), m.data_ptr(), g.data_ptr(), n, c, dout.data_ptr(),
+                  _stream(), cost=(4 * n * (3 * c + 1), 4 * n * c, ""))
+        return dout, None, None
+
+
+def masked_l1_loss(out, color, mask):
+    """The 3D trainer's training loss as one forward and one backward kernel (drop-in for its torch.where / L1Loss / pow /
+    mean chain on CUDA tensors)."""
+    return MaskedL1Fn.apply(out, color, mask)

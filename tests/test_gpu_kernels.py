@@ -472,3 +472,42 @@ def test_unpool_concat_writes_the_skip_concatenation_in_place(ca, cb):
     assert torch.equal(out.cpu(), ref)
     assert torch.equal(sd.grad.cpu(), sr.grad)
     assert rel_err(xd.grad, xr.grad) <= TOL         # segmented sum in member order vs index_add order: same values up to rounding
+
+
+@pytest.mark.parametrize("n,c", [(1000, 64), (4099, 16), (77, 256), (20000, 32)])
+def test_head_tanh_kernel(n, c):
+    """tanh(h W^T + b) with the 3-wide Linear in registers (stinet_head_*) against torch in fp64: output, dh, dW, db."""
+    from stinet_b200 import ops
+    g = torch.Generator().manual_seed(n + c)
+    h = torch.randn(n, c, generator=g)
+    w, b = torch.randn(3, c, generator=g) / c ** 0.5, torch.randn(3, generator=g)
+    go = torch.randn(n, 3, generator=g)
+    hr, wr, br = (t.double().requires_grad_(True) for t in (h, w, b))
+    ref = torch.tanh(hr @ wr.t() + br)
+    ref.backward(go.double())
+    hd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (h, w, b))
+    out = ops.head_tanh(hd, wd, bd)
+    assert out is not None
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= TOL and rel_err(hd.grad, hr.grad) <= TOL
+    assert rel_err(wd.grad, wr.grad) <= TOL and rel_err(bd.grad, br.grad) <= TOL
+
+
+@pytest.mark.parametrize("n", [1000, 40962])
+def test_masked_l1_loss_kernel(n):
+    """The trainer's loss (trainers/inpainting3d_trainer.py:127-137) as one kernel each way against the torch chain."""
+    from stinet_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    out = torch.tanh(torch.randn(n, 3, generator=g))
+    color = torch.rand(n, 3, generator=g) * 2 - 1
+    mask = torch.randint(0, 12, (n, 1), generator=g).float() * (torch.rand(n, 1, generator=g) > 0.4)
+    out[:5] = color[:5]                                                      # exact ties: sign(0) = 0 on both sides
+    orf = out.double().requires_grad_(True)
+    composed = torch.where((mask > 0).expand_as(color), orf, color.double())
+    ref = ((composed - color.double()).abs() * torch.pow(0.99, mask.squeeze().double()).unsqueeze(1)).mean()
+    (ref * 3.0).backward()
+    od = out.to(DEV).requires_grad_(True)
+    loss = ops.masked_l1_loss(od, color.to(DEV), mask.to(DEV))
+    (loss * 3.0).backward()
+    assert rel_err(loss, ref) <= TOL and rel_err(od.grad, orf.grad) <= TOL
+    assert bool((od.grad[(mask.squeeze() <= 0).to(DEV)] == 0).all())
