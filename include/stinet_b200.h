@@ -182,8 +182,12 @@ int stinet_segnorm_stats(const float* x, int64_t ldx, int64_t n_rows, int64_t ch
 int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
                        int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, float eps,
                        const float* residual, int64_t ldr, int act, float* out, int64_t ldo, float* mean, float* rstd,
-                       float* amax_out, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
-/* amax_out (nullable, float[1], here and in stinet_segnorm_bwd): the kernels also leave max|out| (max|dx|) there -- the
+                       float* amax_out, void* out_hi, void* out_lo, int64_t ldp, const float* res_amax, int32_t* out_exp,
+                       void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+/* out_hi / out_lo / ldp / out_exp (nullable group): the same pass also writes `out` as fp16 operand planes for the dense
+ * layer that reads it next (no split pass later).  Their scale comes from the bound max|residual| + sqrt(longest slice)
+ * (res_amax: float[1] holding max|residual| or a bound of it; required when a residual is given).  Vector path only.
+ * amax_out (nullable, float[1], here and in stinet_segnorm_bwd): the kernels also leave max|out| (max|dx|) there -- the
  * plane scale of the dense layer that reads the result next (stinet_f16_split) -- at no extra pass over the data. */
 /* out = residual + act((x - mean[g]) * rstd[g])   (residual nullable; act = STINET_ACT_*): the tail of
  * GraphResnetBlock.forward, models/surfacetextureinpaintingnet.py:510-521.  g = gid[r] (NULL: segment 0);
@@ -313,6 +317,20 @@ int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* 
 /* dp_colsum (nullable, float[hidden]): also sum_i dP[i,:], the bias gradient of the hoisted first Linear, accumulated by the
  * kernel that produces dP (per-CTA partials in `workspace`, fixed-order second stage). */
 size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden);
+
+/* ---- operand planes of ALL dense-layer weights of a network in two launches (per step: weights change with every optimizer
+ * step, so their planes are re-split once per forward and shared by fwd / dgrad / wgrad of that step).  The caller keeps a
+ * table of entries in device memory -- built on the host with stinet_weight_entry_fill (stinet_weight_entry_bytes() bytes
+ * each, chunk0 = running sum of the returned chunk counts), copied to the device once -- and calls refresh every step.
+ *   kind 0: planes of W [rows, cols];  kind 1: planes of the hoisted first layer [Wa - Wb ; Wb] of EdgeConv (W = [Wa | Wb],
+ *   rows = H, cols = din; models/modules/edge_conv_filter.py:46-57) and bcat = [b ; 0];  kind 2: [-W ; W] of EdgeConvTransInv.
+ *   Planes of kind 1 / 2 have 2*rows rows.  amax / exp: one float / int32 slot per entry. */
+size_t stinet_weight_entry_bytes(void);
+long long stinet_weight_entry_fill(void* host_entry, const float* w, int64_t ldw, const float* b, int64_t rows, int64_t cols,
+                                 int kind, void* hi, void* lo, int64_t ldp, float* bcat, float* amax, int32_t* exp,
+                                 int64_t chunk0);
+int stinet_weight_planes_refresh(const void* device_table, int n_entries, int64_t n_chunks, float* amax_slots,
+                                 stinet_stream_t stream);
 
 /* ---- the tail of the network and the trainer's loss
  *   head        out[N,3] = tanh(h[N,C] W^T + b), W [3,C] -- reference models/surfacetextureinpaintingnet.py:466-469

@@ -70,3 +70,124 @@ extern "C" int stinet_edgeconv_hoist_bwd(const float* dWcat, const float* dbcat,
   K(hoist_bwd_kernel<<<wave_grid(hidden * din, 256 * 4, 8), 256, 0, s>>>(dWcat, dbcat, hidden, din, trans_inv, dW, ldw, db));
   return check_launch("edgeconv_hoist_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operand planes of ALL dense-layer weights of a network in two launches per step (instead of amax + split [+ hoist] per
+// weight): a device table lists the weights, each CTA works on one 4096-element chunk of one weight.
+//   kind 0: planes of W [rows, cols] itself (second Linear of a conv, shortcut, head)
+//   kind 1: planes of the hoisted first layer  Wcat = [Wa - Wb ; Wb]  of EdgeConv, W = [Wa | Wb] [H, 2 din]   (+ bcat = [b ; 0])
+//   kind 2: planes of  Wcat = [-W ; W]  of EdgeConvTransInv, W [H, din]                                        (+ bcat = [b ; 0])
+// Pass 1 takes max|.| of the values that will be split (atomicMax of bit patterns into the entry's slot, zeroed by a
+// memset), pass 2 reads it, scales and splits (csrc/common.cuh: split_one) and publishes the exponent.
+namespace stinet {
+
+struct WeightEntry {
+  const float* w;        // source weight, row pitch ldw
+  const float* b;        // kind 1/2: bias of the first Linear (nullable)
+  __half* hi;            // planes [out_rows, ldp]
+  __half* lo;            // nullable (one-pass mode)
+  float* bcat;           // kind 1/2: [2H] (nullable)
+  unsigned* amax;        // slot
+  int32_t* exp;          // slot
+  int64_t ldw, ldp;
+  int32_t rows, cols;    // of the SOURCE view that is walked: kind 0: W; kind 1/2: H x din
+  int32_t kind, chunk0;  // first global chunk index of this entry
+};
+constexpr int kWChunk = 4096;
+
+__device__ __forceinline__ int find_entry(const WeightEntry* __restrict__ tab, int n_entries, int chunk) {
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {                         // last entry with chunk0 <= chunk
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].chunk0 <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// the (up to two) values a source element contributes: kind 0: (w, -); kind 1: (wa - wb, wb); kind 2: (-w, w)
+__device__ __forceinline__ void weight_values(const WeightEntry& e, int64_t r, int64_t c, float& p, float& q) {
+  if (e.kind == 0) {
+    p = e.w[r * e.ldw + c];
+    q = 0.f;
+  } else if (e.kind == 1) {
+    const float wa = e.w[r * e.ldw + c];
+    q = e.w[r * e.ldw + e.cols + c];
+    p = wa - q;
+  } else {
+    q = e.w[r * e.ldw + c];
+    p = -q;
+  }
+}
+
+__global__ void __launch_bounds__(256) wplanes_amax_kernel(const WeightEntry* __restrict__ tab, int n_entries) {
+  const int ei = find_entry(tab, n_entries, blockIdx.x);
+  const WeightEntry e = tab[ei];
+  const int64_t total = (int64_t)e.rows * e.cols;
+  const int64_t base = (int64_t)(blockIdx.x - e.chunk0) * kWChunk;
+  unsigned m = 0u;
+  for (int64_t idx = base + threadIdx.x; idx < min(total, base + kWChunk); idx += 256) {
+    const int64_t r = idx / e.cols, c = idx - r * e.cols;
+    float p, q;
+    weight_values(e, r, c, p, q);
+    m = max(max(m, __float_as_uint(p) & 0x7FFFFFFFu), __float_as_uint(q) & 0x7FFFFFFFu);
+  }
+  amax_publish(m, e.amax);
+}
+
+__global__ void __launch_bounds__(256) wplanes_split_kernel(const WeightEntry* __restrict__ tab, int n_entries) {
+  const int ei = find_entry(tab, n_entries, blockIdx.x);
+  const WeightEntry e = tab[ei];
+  const int64_t total = (int64_t)e.rows * e.cols;
+  const int64_t base = (int64_t)(blockIdx.x - e.chunk0) * kWChunk;
+  const int sft = plane_shift(*e.amax);
+  const float scale = plane_scale(sft);
+  if (blockIdx.x == e.chunk0 && threadIdx.x == 0) *e.exp = -sft;
+  for (int64_t idx = base + threadIdx.x; idx < min(total, base + kWChunk); idx += 256) {
+    const int64_t r = idx / e.cols, c = idx - r * e.cols;
+    float p, q;
+    weight_values(e, r, c, p, q);
+    __half h, l;
+    split_one(p, scale, h, l);
+    e.hi[r * e.ldp + c] = h;
+    if (e.lo) e.lo[r * e.ldp + c] = l;
+    if (e.kind != 0) {
+      split_one(q, scale, h, l);
+      e.hi[(r + e.rows) * e.ldp + c] = h;
+      if (e.lo) e.lo[(r + e.rows) * e.ldp + c] = l;
+      if (e.bcat && c == 0) {
+        e.bcat[r] = e.b ? e.b[r] : 0.f;
+        e.bcat[e.rows + r] = 0.f;
+      }
+    }
+  }
+}
+
+}  // namespace stinet
+
+extern "C" size_t stinet_weight_entry_bytes(void) { return sizeof(stinet::WeightEntry); }
+
+// Fill one table entry on the HOST (the caller copies the table to the device once and reuses it every step).
+// Returns the number of 4096-element chunks the entry occupies.
+extern "C" long long stinet_weight_entry_fill(void* host_entry, const float* w, int64_t ldw, const float* b, int64_t rows,
+                                            int64_t cols, int kind, void* hi, void* lo, int64_t ldp, float* bcat, float* amax,
+                                            int32_t* exp, int64_t chunk0) {
+  stinet::WeightEntry* e = static_cast<stinet::WeightEntry*>(host_entry);
+  e->w = w; e->b = b; e->hi = static_cast<__half*>(hi); e->lo = static_cast<__half*>(lo); e->bcat = bcat;
+  e->amax = reinterpret_cast<unsigned*>(amax); e->exp = exp; e->ldw = ldw; e->ldp = ldp;
+  e->rows = (int32_t)rows; e->cols = (int32_t)cols; e->kind = kind; e->chunk0 = (int32_t)chunk0;
+  return ceil_div(rows * cols > 0 ? rows * cols : 1, stinet::kWChunk);
+}
+
+extern "C" int stinet_weight_planes_refresh(const void* device_table, int n_entries, int64_t n_chunks, float* amax_slots,
+                                            stinet_stream_t stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  STINET_REQUIRE(n_entries >= 0 && n_chunks >= 0 && n_chunks < (1ll << 31), STINET_ERR_ARG, "weight_planes_refresh: bad size");
+  if (n_entries == 0) return STINET_OK;
+  STINET_REQUIRE(device_table && amax_slots, STINET_ERR_ARG, "weight_planes_refresh: null pointer");
+  cudaError_t e = cudaMemsetAsync(amax_slots, 0, sizeof(float) * (size_t)n_entries, s);
+  STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "weight_planes_refresh: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  const stinet::WeightEntry* tab = static_cast<const stinet::WeightEntry*>(device_table);
+  K(stinet::wplanes_amax_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(tab, n_entries));
+  K(stinet::wplanes_split_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(tab, n_entries));
+  return check_launch("weight_planes_refresh");
+}

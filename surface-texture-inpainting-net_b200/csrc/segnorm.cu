@@ -22,6 +22,24 @@ constexpr int kTileGroups = 32;   // channel groups (float4 or scalar) per CTA t
 
 enum { MODE_SUM = 0, MODE_CSQ = 1, MODE_BWD = 2 };
 
+// Optional second form of a forward result: fp16 operand planes for the dense layer that reads it next (include/
+// stinet_b200.h, "dense layers on operand PLANES"), written by the same pass that writes the fp32 rows.  The scale must be
+// known before the first row is written, so it comes from an upper bound:  |residual + act(yhat)| <= max|residual| + add,
+// add = sqrt(longest slice) (|yhat| <= sqrt(n) for a biased-variance norm over n rows; ELU keeps |.| below max(1, yhat)).
+struct PlaneOut {
+  __half* hi; __half* lo; int64_t ldp;     // hi == nullptr: no planes
+  const float* res_amax;                    // nullable: max|residual| (exact or a bound); no residual: nullptr
+  float add;
+  int32_t* exp_out;
+};
+__device__ __forceinline__ float plane_out_scale(const PlaneOut& po, bool writer) {
+  if (po.hi == nullptr) return 0.f;
+  const float bound = (po.res_amax ? __ldg(po.res_amax) : 0.f) + po.add;
+  const int sft = plane_shift(__float_as_uint(bound));
+  if (writer) *po.exp_out = -sft;
+  return plane_scale(sft);
+}
+
 struct NormArgs {
   const float* x; int64_t ldx;
   const float* dout; int64_t ldg;
@@ -247,7 +265,8 @@ __global__ void __launch_bounds__(kNormThreads)
 segnorm_slice_apply_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ aux, int64_t lda,
                            const int32_t* __restrict__ slice_ptr, int channels, const float* __restrict__ mean,
                            const float* __restrict__ rstd, const float* __restrict__ s1, const float* __restrict__ s2,
-                           int act, float* __restrict__ out, int64_t ldo, unsigned* __restrict__ amax_out) {
+                           int act, float* __restrict__ out, int64_t ldo, unsigned* __restrict__ amax_out, PlaneOut po) {
+  const float pscale = plane_out_scale(po, blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0);
   const int groups = channels >> 2;
   const int txw = min(groups, kTileGroups);
   const int tyn = kNormThreads / txw;
@@ -301,6 +320,8 @@ segnorm_slice_apply_kernel(const float* __restrict__ x, int64_t ldx, const float
         const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
         amax_bits = amax4(amax_bits, ov);
         st_stream(reinterpret_cast<float4*>(out + (int64_t)r * ldo) + grp, ov);
+        if (!BWD && po.hi != nullptr)
+          split_store4(ov, pscale, po.hi + (int64_t)r * po.ldp + 4 * grp, po.lo ? po.lo + (int64_t)r * po.ldp + 4 * grp : nullptr);
       }
     }
   }
@@ -322,6 +343,7 @@ struct FusedArgs {
   float* out; int64_t ldo;
   int channels; int act; float eps;
   unsigned* amax_out;                  // nullable: max |out| as a bit pattern (atomicMax into a zeroed slot)
+  PlaneOut po;                         // fwd: optional fp16 planes of out
 };
 
 __device__ __forceinline__ float4 f4add(const float4& a, const float4& b) {
@@ -422,12 +444,15 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_fwd_kernel(FusedAr
     reinterpret_cast<float4*>(a.rstd + (int64_t)s * a.channels)[c4] = rs;
   }
   unsigned amax_bits = 0u;
+  const float pscale = plane_out_scale(a.po, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
   auto finish = [&](const float4& xv, int r) {
     float4 o = make_float4((xv.x - m.x) * rs.x, (xv.y - m.y) * rs.y, (xv.z - m.z) * rs.z, (xv.w - m.w) * rs.w);
     if (a.act == STINET_ACT_ELU) { o.x = elu1(o.x); o.y = elu1(o.y); o.z = elu1(o.z); o.w = elu1(o.w); }
     if (a.aux) o = f4add(o, reinterpret_cast<const float4*>(a.aux + (int64_t)r * a.lda)[c4]);
     amax_bits = amax4(amax_bits, o);
     reinterpret_cast<float4*>(a.out + (int64_t)r * a.ldo)[c4] = o;
+    if (a.po.hi != nullptr)
+      split_store4(o, pscale, a.po.hi + (int64_t)r * a.po.ldp + 4 * c4, a.po.lo ? a.po.lo + (int64_t)r * a.po.ldp + 4 * c4 : nullptr);
   };
   if (RR > 0) {
 #pragma unroll
@@ -809,10 +834,19 @@ extern "C" int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows,
 extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, int64_t channels, int64_t n_seg,
                                   int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt, float eps,
                                   const float* residual, int64_t ldr, int act, float* out, int64_t ldo, float* mean,
-                                  float* rstd, float* amax_out, void* workspace, size_t workspace_bytes,
+                                  float* rstd, float* amax_out, void* out_hi, void* out_lo, int64_t ldp,
+                                  const float* res_amax, int32_t* out_exp, void* workspace, size_t workspace_bytes,
                                   stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   unsigned* am = reinterpret_cast<unsigned*>(amax_out);
+  const float nrm = sqrtf((float)(max_seg_rows > 1 ? max_seg_rows : 1));
+  PlaneOut po{static_cast<__half*>(out_hi), static_cast<__half*>(out_lo), ldp, res_amax,
+              act == STINET_ACT_ELU ? fmaxf(1.f, nrm) : nrm, out_exp};
+  if (out_hi != nullptr) {
+    STINET_REQUIRE(out_exp && ldp >= channels && ldp % 8 == 0 && aligned16(out_hi) && (!out_lo || aligned16(out_lo)) &&
+                       (residual == nullptr || res_amax != nullptr),
+                   STINET_ERR_ARG, "segnorm_fwd: plane output needs exp, a pitch %% 8 == 0 and max|residual|");
+  }
   if (am != nullptr) {
     cudaError_t e = cudaMemsetAsync(am, 0, sizeof(unsigned), s);
     STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "segnorm_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
@@ -825,7 +859,7 @@ extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, i
   const bool vec = nvec(channels, {x, out, residual, mean, rstd}, {ldx, ldo, residual ? ldr : 0});
   if (vec && max_seg_rows <= kFusedMaxRows) {
     const FusedPlan pl = fused_plan(max_seg_rows);
-    FusedArgs a{x, ldx, residual, ldr, slice_ptr, cnt, mean, rstd, out, ldo, (int)channels, act, eps, am};
+    FusedArgs a{x, ldx, residual, ldr, slice_ptr, cnt, mean, rstd, out, ldo, (int)channels, act, eps, am, po};
     return pl.cached ? launch_fused(segnorm_fused_fwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
                      : launch_fused(segnorm_fused_fwd_kernel<0>, a, n_seg, pl.cluster, s);
   }
@@ -837,9 +871,10 @@ extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, i
     const int tyn = kNormThreads / (groups < kTileGroups ? groups : kTileGroups);
     dim3 grid((unsigned)ceil_div(max_seg_rows, tyn * kApplyU * 2), (unsigned)n_seg, (unsigned)ceil_div(groups, kTileGroups));
     K(segnorm_slice_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, residual, ldr, slice_ptr, (int)channels, mean,
-                                                                      rstd, nullptr, nullptr, act, out, ldo, am));
+                                                                      rstd, nullptr, nullptr, act, out, ldo, am, po));
     return check_launch("segnorm_fwd");
   }
+  STINET_REQUIRE(out_hi == nullptr, STINET_ERR_UNSUPPORTED, "segnorm_fwd: plane output needs the vector path (channels %% 4 == 0, aligned rows)");
   // odd widths: the per-row lookup kernel needs a graph id; a single slice uses id 0
   STINET_REQUIRE(n_seg == 1, STINET_ERR_UNSUPPORTED, "segnorm_fwd: channel count %lld (not a multiple of 4) with %lld slices",
                  (long long)channels, (long long)n_seg);
@@ -872,7 +907,7 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     STINET_REQUIRE(slice_ptr && cnt && n_seg > 0 && n_seg <= 65535, STINET_ERR_ARG, "segnorm_bwd: segments required");
     const FusedPlan pl = fused_plan(max_seg_rows);
     FusedArgs a{x, ldx, dout, ldg, slice_ptr, cnt, const_cast<float*>(mean), const_cast<float*>(rstd), dx, lddx,
-                (int)channels, act, 0.f, am};
+                (int)channels, act, 0.f, am, PlaneOut{nullptr, nullptr, 0, nullptr, 0.f, nullptr}};
     return pl.cached ? launch_fused(segnorm_fused_bwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
                      : launch_fused(segnorm_fused_bwd_kernel<0>, a, n_seg, pl.cluster, s);
   }
@@ -894,7 +929,8 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     const int tyn = kNormThreads / (groups < kTileGroups ? groups : kTileGroups);
     dim3 grid2((unsigned)ceil_div(max_seg_rows, tyn * kApplyU * 2), (unsigned)n_seg, (unsigned)ceil_div(groups, kTileGroups));
     K(segnorm_slice_apply_kernel<true><<<grid2, kNormThreads, 0, s>>>(x, ldx, dout, ldg, slice_ptr, (int)channels, mean, rstd,
-                                                                      s1, s2, act, dx, lddx, am));
+                                                                      s1, s2, act, dx, lddx, am,
+                                                                      PlaneOut{nullptr, nullptr, 0, nullptr, 0.f, nullptr}));
     return check_launch("segnorm_bwd");
   }
   const int grid = wave_grid(n_rows * (channels / (vec ? 4 : 1)), kNormThreads * 4, 8, 8);

@@ -44,7 +44,7 @@ SIGNATURES = {
     "stinet_unpool_bwd": (I, [P, I64, P, P, I64, I64, P, I64, P]),
     "stinet_segnorm_workspace_bytes": (SZ, [I64, I64, I64]),
     "stinet_segnorm_stats": (I, [P, I64, I64, I64, I64, I64, P, P, P, F, P, P, P, SZ, P]),
-    "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, P, SZ, P]),
+    "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, P, P, I64, P, P, P, SZ, P]),
     "stinet_segnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, I64, P]),
     "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, P, SZ, P]),
     "stinet_affnorm_workspace_bytes": (SZ, [I64, I64, I64]),
@@ -52,6 +52,9 @@ SIGNATURES = {
     "stinet_affnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, P, P, P, I64, P]),
     "stinet_affnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, I, P, P, P, P, P, I64, P, P, P, P, SZ, P]),
     "stinet_bn_running_update": (I, [P, P, I64, F, F, I64, P, P, P]),
+    "stinet_weight_entry_bytes": (SZ, []),
+    "stinet_weight_entry_fill": (I64, [P, P, I64, P, I64, I64, I, P, P, I64, P, P, P, I64]),
+    "stinet_weight_planes_refresh": (I, [P, I, I64, P, P]),
     "stinet_head_workspace_bytes": (SZ, [I64, I64]),
     "stinet_head_fwd": (I, [P, I64, P, P, I64, I64, P, P]),
     "stinet_head_bwd": (I, [P, I64, P, P, P, I64, I64, P, I64, P, P, P, SZ, P]),

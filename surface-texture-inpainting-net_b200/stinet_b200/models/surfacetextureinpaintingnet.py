@@ -186,6 +186,25 @@ class SurfaceTextureInpaintingNet(nn.Module):
                 m.precision = self.io_precision
         return self
 
+    def _refresh_weight_planes(self):
+        """fp16 operand planes of every dense-layer weight (hoisted first layers included) in two launches per forward."""
+        wp = getattr(self, "_wplanes", None)
+        if wp is None:
+            entries = []
+            for m in self.modules():
+                if isinstance(m, edge_conv_filter.EdgeConv) and m.hoistable:
+                    lin0, lin2 = m.nn[0], m.nn[2]
+                    din = lin0.in_features if m.trans_inv else lin0.in_features // 2
+                    if din % 4 == 0 and lin0.out_features % 4 == 0 and lin2.out_features % 4 == 0:
+                        entries.append((lin0.weight, lin0.bias, 2 if m.trans_inv else 1))
+                        entries.append((lin2.weight, None, 0))
+                elif isinstance(m, GraphResnetBlock) and hasattr(m, 'shortcut') and m.shortcut.in_features % 4 == 0 \
+                        and m.shortcut.out_features % 4 == 0:
+                    entries.append((m.shortcut.weight, None, 0))
+            entries.append((self.final_linear1.weight, None, 0))
+            wp = self._wplanes = ops.WeightPlanes(entries)
+        wp.refresh()
+
     def _pooling(self, vertex_features, cluster):
         if self._pooling_type == 'mean':
             return ops.pool_mean(vertex_features, cluster)
@@ -205,6 +224,9 @@ class SurfaceTextureInpaintingNet(nn.Module):
 
         def seg(level):
             return cache.segments(level, True) if per_graph else whole[level]
+
+        if sample.x.is_cuda and self.precision in ('fp32', 'f16'):
+            self._refresh_weight_planes()
 
         out = sample.x
         e0 = cache.edges('edge_index', 0)

@@ -124,6 +124,10 @@ def planes_of(t: torch.Tensor, need_lo: bool = True) -> Planes:
     # Parameters are never cached: fused / foreach optimizers update them without touching the version counter, so a
     # split taken in one step says nothing about the next one (one split per forward, shared with backward through ctx)
     cacheable = not (t.is_leaf and t.requires_grad)
+    if not cacheable:
+        wp = _weight_planes(t, 0)                    # split by this forward's WeightPlanes.refresh()
+        if wp is not None:
+            return wp[0]
     cached = getattr(t, "_stinet_planes", None) if cacheable else None
     if cached is not None and cached[0] == t._version and cached[1] == _plane_epoch and (cached[2].lo is not None or not need_lo):
         return cached[2]
@@ -148,6 +152,68 @@ def planes_of(t: torch.Tensor, need_lo: bool = True) -> Planes:
     if cacheable:
         t._stinet_planes = (t._version, _plane_epoch, p)
     return p
+
+
+_weight_epoch = 0
+
+
+class WeightPlanes:
+    """Operand planes of all dense-layer weights of a module, refreshed in two launches per forward (the weights change
+    with every optimizer step; fused optimizers do not touch version counters, so nothing is cached across steps).
+    entries: (weight Parameter, bias Parameter or None, kind) with kind 0 = the weight itself, 1 = hoisted EdgeConv first
+    layer [Wa - Wb ; Wb], 2 = hoisted EdgeConvTransInv first layer [-W ; W] (both with bcat = [b ; 0])."""
+
+    def __init__(self, entries):
+        self.entries = [(w, b, int(k)) for w, b, k in entries]
+        self._key = None
+
+    def _build(self, dev):
+        n = len(self.entries)
+        self.amax = torch.zeros(max(n, 1), dtype=torch.float32, device=dev)
+        self.exp = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        esz = _abi.query("stinet_weight_entry_bytes")
+        import ctypes
+        host = (ctypes.c_char * (esz * max(n, 1)))()
+        self.planes, chunk0 = [], 0
+        lib = _abi.load()
+        for i, (w, b, kind) in enumerate(self.entries):
+            assert w.dim() == 2 and w.stride(1) == 1 and w.dtype == torch.float32
+            rows = w.shape[0]
+            cols = w.shape[1] if kind != 1 else w.shape[1] // 2
+            out_rows = rows if kind == 0 else 2 * rows
+            p = _new_planes(out_rows, cols, True, dev)
+            p.exp = self.exp[i:i + 1]
+            bcat = torch.empty(2 * rows, dtype=torch.float32, device=dev) if kind != 0 else None
+            self.planes.append((p, bcat))
+            chunk0 += int(lib.stinet_weight_entry_fill(
+                ctypes.addressof(host) + i * esz, w.data_ptr(), w.stride(0), _ptr(b), rows, cols, kind, p.hi.data_ptr(),
+                p.lo.data_ptr(), p.ld, _ptr(bcat), self.amax[i:i + 1].data_ptr(), self.exp[i:i + 1].data_ptr(), chunk0))
+        self.n_chunks = chunk0
+        self.table = torch.frombuffer(host, dtype=torch.uint8).clone().to(dev)
+
+    def refresh(self):
+        """Split every weight of the table (2 launches) and stamp the parameters with their fresh planes."""
+        global _weight_epoch
+        if not self.entries:
+            return
+        dev = self.entries[0][0].device
+        key = tuple((w.data_ptr(), None if b is None else b.data_ptr()) for w, b, _ in self.entries)
+        if key != self._key:                         # first use, or the parameters moved (.to(), load with assign=True)
+            self._build(dev)
+            self._key = key
+        _abi.call("stinet_weight_planes_refresh", self.table.data_ptr(), len(self.entries), self.n_chunks, self.amax.data_ptr(),
+                  _stream(), cost=(12 * sum(w.numel() for w, _, _ in self.entries), 0, ""))
+        _weight_epoch += 1
+        for (w, _, kind), (p, bcat) in zip(self.entries, self.planes):
+            w._stinet_wp = (_weight_epoch, kind, p, bcat)
+
+
+def _weight_planes(w: torch.Tensor, kind: int):
+    """(planes, bcat) stamped by a WeightPlanes.refresh() of the CURRENT forward, else None."""
+    wp = getattr(w, "_stinet_wp", None)
+    if wp is not None and wp[0] == _weight_epoch and wp[1] == kind:
+        return wp[2], wp[3]
+    return None
 
 
 def _new_planes(rows: int, cols: int, need_lo: bool, dev) -> Planes:
@@ -253,11 +319,13 @@ def _bwd_passes(passes: int) -> int:
 class LinearPlanesFn(Function):
     """y = x W^T + b on fp16 operand planes (tcgen05 kind::f16; passes = 3: fp32-class result, 1: 11-bit operands)."""
 
+    last_amax = None      # max|y| of the most recent forward (from the GEMM's epilogue), picked up by linear(want_amax=True)
+
     @staticmethod
     def forward(ctx, x, weight, bias, rowmask, passes):
         need_lo = _bwd_passes(passes) == 3
         xp, wp = planes_of(x, need_lo), planes_of(weight, need_lo)
-        y, _ = _pl_fwd(xp, wp, bias, rowmask, passes)
+        y, LinearPlanesFn.last_amax = _pl_fwd(xp, wp, bias, rowmask, passes, want_amax=True)
         ctx.xp, ctx.wp, ctx.rowmask = xp, wp, rowmask
         ctx.has_bias, ctx.passes = bias is not None, passes
         return y
@@ -303,11 +371,17 @@ class EdgeConvFn(Function):
         kin = w0m.shape[1]
         assert kin == (din if trans_inv else 2 * din) and n == csr.n
         dout = w2.shape[0]
-        wcat = torch.empty((2 * h, din), dtype=torch.float32, device=dev)
-        bcat = torch.empty((2 * h,), dtype=torch.float32, device=dev) if b0 is not None else None
-        _abi.call("stinet_edgeconv_hoist_fwd", w0m.data_ptr(), _ld(w0m), _ptr(b0), h, din, int(trans_inv), wcat.data_ptr(),
-                  _ptr(bcat), s, cost=(4 * h * (kin + 2 * din), 0, ""))
-        wcp = planes_of(wcat, need_lo)
+        hp = _weight_planes(w0, 2 if trans_inv else 1)
+        if hp is not None:                           # hoisted and split by this forward's WeightPlanes.refresh()
+            wcp, bcat = hp
+            if b0 is None:
+                bcat = None
+        else:
+            wcat = torch.empty((2 * h, din), dtype=torch.float32, device=dev)
+            bcat = torch.empty((2 * h,), dtype=torch.float32, device=dev) if b0 is not None else None
+            _abi.call("stinet_edgeconv_hoist_fwd", w0m.data_ptr(), _ld(w0m), _ptr(b0), h, din, int(trans_inv), wcat.data_ptr(),
+                      _ptr(bcat), s, cost=(4 * h * (kin + 2 * din), 0, ""))
+            wcp = planes_of(wcat, need_lo)
         pq, pq_amax = _pl_fwd(xp, wcp, bcat, None, passes, want_amax=True)
         if _edge_message_observer is not None:
             _edge_message_observer(pq, csr)
@@ -374,6 +448,15 @@ def edge_conv(x, w0, b0, w2, b2, csr, trans_inv: bool, precision: str):
 
 
 def linear(x, weight, bias=None, rowmask=None, precision="fp32"):
+    y = _linear(x, weight, bias, rowmask, precision)
+    if LinearPlanesFn.last_amax is not None:         # the GEMM's epilogue left max|y| behind: consumers scale planes with it
+        if y.dim() == 2 and y.is_contiguous():
+            set_amax(y, LinearPlanesFn.last_amax)
+        LinearPlanesFn.last_amax = None
+    return y
+
+
+def _linear(x, weight, bias=None, rowmask=None, precision="fp32"):
     """y = x W^T + b.  TMA (the tensor-core path) needs 16-byte row pitches, so a reduction width or an output width
     that is not a multiple of 4 floats (the 10-channel input, the 3-channel head) is zero-padded: the extra products
     are exact zeros and the extra output columns are sliced away again."""
@@ -691,6 +774,8 @@ def unpool(xc, cl):
 class NormActResFn(Function):
     """out = residual + act(instance_norm(x; segments))   (use_norm=False: identity norm)."""
     last_amax = None      # device scalar max|out| of the most recent forward (picked up by norm_act_res)
+    last_planes = None    # fp16 operand planes of the most recent forward's output, when the kernels wrote them
+    emit_planes = True
 
     @staticmethod
     def forward(ctx, x, residual, seg: Optional[Segments], use_norm: bool, act: int, eps: float):
@@ -712,10 +797,22 @@ class NormActResFn(Function):
             # slices are the graphs: one entry point (a single cluster kernel when the slices are short); the kernels also
             # leave max|out| behind: the next dense layer's operand planes are scaled with it
             amax = torch.empty(1, dtype=torch.float32, device=dev)
+            # ... and, when max|residual| is known, the result also as fp16 operand planes (scale from the bound
+            # max|residual| + sqrt(rows)): the block that reads it next splits nothing
+            planes = None
+            res_amax = None
+            if residual is not None:
+                known = getattr(residual, "_stinet_amax", None)
+                res_amax = known[1] if (known is not None and known[0] == residual._version) else None
+            if _vec_ok(c, x, res) and c % 4 == 0 and (residual is None or res_amax is not None) and NormActResFn.emit_planes:
+                planes = _new_planes(n, c, True, dev)
             _abi.call("stinet_segnorm_fwd", x.data_ptr(), _ld(x), n, c, seg.n_seg, seg.max_seg_rows,
                       seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(), float(eps), _ptr(res),
                       _ld(res) if res is not None else 0, act, out.data_ptr(), c, mean.data_ptr(), rstd.data_ptr(),
-                      amax.data_ptr(), ws.data_ptr(), nb, _stream(), cost=(4 * n * c * (3 + nres), 7 * n * c, f"C{c}"))
+                      amax.data_ptr(), _ptr(planes.hi) if planes else None, _ptr(planes.lo) if planes else None,
+                      planes.ld if planes else 0, _ptr(res_amax), _ptr(planes.exp) if planes else None,
+                      ws.data_ptr(), nb, _stream(), cost=(4 * n * c * (3 + nres + (1 if planes else 0)), 7 * n * c, f"C{c}"))
+            NormActResFn.last_planes = planes
         else:
             if use_norm:
                 # the reference's linspace slices cut across graphs (ragged batch), or rows of an odd width: sums by
@@ -802,6 +899,9 @@ def norm_act_res(x, residual, seg, use_norm=True, act=ACT_ELU, eps=1e-5):
     if NormActResFn.last_amax is not None:
         set_amax(out, NormActResFn.last_amax)        # max|out| came with the norm kernels: no reduction pass later
         NormActResFn.last_amax = None
+    if NormActResFn.last_planes is not None:         # ... and so did its operand planes: no split pass either
+        out._stinet_planes = (out._version, _plane_epoch, NormActResFn.last_planes)
+        NormActResFn.last_planes = None
     return out
 
 
