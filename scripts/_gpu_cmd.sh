@@ -1,6 +1,10 @@
 OUT=gpurun_out
-( timeout 900 python -m pytest tests/test_gpu_engine.py tests/test_gpu_structure.py -m gpu -q --tb=short -p no:cacheprovider ) > $OUT/pytest_r2_j.log 2>&1; echo "pytest exit $?"; tail -15 $OUT/pytest_r2_j.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > $OUT/bench_n2_r2_j.json 2> $OUT/bench_n2_r2_j.err; echo "bench n2 exit $?"
-python -c "import json;b=json.load(open('$OUT/bench_n2_r2_j.json'));print('N=2', b['value'], b['ms_per_step'], b['e2e']['ms_per_step'])" || tail -30 $OUT/bench_n2_r2_j.err
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_n1_r2_j.json 2> $OUT/bench_n1_r2_j.err; python -c "import json;b=json.load(open('$OUT/bench_n1_r2_j.json'));print('N=1', b['value'], b['ms_per_step'], b['e2e']['ms_per_step'])"
-STINET_ALLREDUCE_IN_GRAPH=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --no-cached > $OUT/bench_n2_out_r2_j.json 2> $OUT/bench_n2_out_r2_j.err; python -c "import json;b=json.load(open('$OUT/bench_n2_out_r2_j.json'));print('N=2 out-of-graph', b['value'], b['ms_per_step'])" || tail -20 $OUT/bench_n2_out_r2_j.err
+timeout 600 python scripts/gemm_f16_check.py --regimes unit > $OUT/gemm_f16_r2_m.jsonl 2> $OUT/gemm_f16_r2_m.err; echo "check exit $?"; grep -c FAILED $OUT/gemm_f16_r2_m.jsonl
+python - <<'PY'
+import json
+rows=[json.loads(l) for l in open('gpurun_out/gemm_f16_r2_m.jsonl')]
+for r in rows:
+    if r.get('passes')==3 and 'err' in r: print(f"{r['op']:6s} {r['M']:7d} {r['N']:5d} {r['K']:5d} err {r['err']:.1e} ms {r['ms']:.4f} TF {r['TFLOPs']:6.1f} det {r['deterministic']}")
+PY
+( timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -m gpu -q --tb=short -p no:cacheprovider -x ) > $OUT/pytest_r2_m.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/pytest_r2_m.log
+timeout 300 python bench.py --no-cpu-baseline --no-cached > $OUT/bench_r2_m.json 2>$OUT/bench_r2_m.err; python -c "import json;b=json.load(open('gpurun_out/bench_r2_m.json'));print(b['ms_per_step'])"

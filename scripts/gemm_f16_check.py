@@ -63,7 +63,7 @@ def one(op, passes, regime):
             out = torch.full((M, N), float("nan"), device=dev)
             def run():
                 _abi.call("stinet_linear_fwd_f16", xp.hi.data_ptr(), P(xp.lo), xp.ld, xp.exp.data_ptr(), wp.hi.data_ptr(),
-                          P(wp.lo), wp.ld, wp.exp.data_ptr(), b.data_ptr(), mask.data_ptr(), out.data_ptr(), N, M, N, K,
+                          P(wp.lo), wp.ld, wp.exp.data_ptr(), b.data_ptr(), mask.data_ptr(), out.data_ptr(), N, None, M, N, K,
                           passes, ws.data_ptr(), nb, stream)
             def old():
                 _abi.call("stinet_linear_fwd", x.data_ptr(), K, w.data_ptr(), K, b.data_ptr(), mask.data_ptr(),
@@ -73,7 +73,7 @@ def one(op, passes, regime):
             out = torch.full((M, K), float("nan"), device=dev)
             def run():
                 _abi.call("stinet_linear_dgrad_f16", dyp.hi.data_ptr(), P(dyp.lo), dyp.ld, dyp.exp.data_ptr(),
-                          wp.hi.data_ptr(), P(wp.lo), wp.ld, wp.exp.data_ptr(), out.data_ptr(), K, M, N, K, passes,
+                          wp.hi.data_ptr(), P(wp.lo), wp.ld, wp.exp.data_ptr(), out.data_ptr(), K, None, M, N, K, passes,
                           ws.data_ptr(), nb, stream)
             def old():
                 _abi.call("stinet_linear_dgrad", dy.data_ptr(), N, w.data_ptr(), K, out.data_ptr(), K, M, N, K, 0,
@@ -111,7 +111,7 @@ def one(op, passes, regime):
             ops.set_amax(xb, x.abs().max().reshape(1) * 1024.0)
             xq = ops.planes_of(xb, True)
             _abi.call("stinet_linear_fwd_f16", xq.hi.data_ptr(), P(xq.lo), xq.ld, xq.exp.data_ptr(), wp.hi.data_ptr(),
-                      P(wp.lo), wp.ld, wp.exp.data_ptr(), b.data_ptr(), mask.data_ptr(), out.data_ptr(), N, M, N, K,
+                      P(wp.lo), wp.ld, wp.exp.data_ptr(), b.data_ptr(), mask.data_ptr(), out.data_ptr(), N, None, M, N, K,
                       passes, ws.data_ptr(), nb, stream)
             torch.cuda.synchronize()
             rec["err_loose_bound"] = float((out.double() - ref).abs().max() / ref.abs().max())

@@ -454,6 +454,28 @@ __device__ __forceinline__ int dpq_shift(const unsigned* dhid_amax, const float*
 // COLSUM: the CTA also leaves the column sums of the dP rows it produced in colpart[blockIdx.x][hidden] (the bias gradient
 // of the hoisted first Linear is sum_i dP_i; a second stage adds the CTA partials in fixed order).  Needs
 // (gridDim.x * 8) % nchunk == 0, so that a warp keeps one 128-channel chunk for its whole row loop.
+// A warp works on TWO rows per iteration and loads the decision bytes of up to eight in-edges of each before it uses any
+// of them: the kernel is a pure stream (a row of dhid, its mask bytes, a row of planes out), and with one dependent load
+// chain per warp it sat at 0.4 of the HBM rate; sixteen independent loads in flight per lane hide the latency.
+__device__ __forceinline__ float4 masked_count_sum(const uint8_t* __restrict__ mrow, int c4n, int beg, int end, float4 d) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k0 = beg; k0 < end; k0 += 8) {
+    unsigned m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m[u] = (k0 + u < end) ? (unsigned)__ldg(mrow + (int64_t)(k0 + u) * c4n) : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {                       // same order as the one-by-one loop: bit-identical sums
+      if (k0 + u < end) {
+        acc.x += (m[u] & 1u) ? d.x : 0.f;
+        acc.y += (m[u] & 2u) ? d.y : 0.f;
+        acc.z += (m[u] & 4u) ? d.z : 0.f;
+        acc.w += (m[u] & 8u) ? d.w : 0.f;
+      }
+    }
+  }
+  return acc;
+}
+
 template <bool COLSUM>
 __global__ void __launch_bounds__(kAggThreads)
 edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr,
@@ -471,37 +493,39 @@ edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ld
   const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerCta;
   const int c4n = hidden >> 2;
   const int nchunk = (c4n + 31) >> 5;
-  for (int64_t it = warp0; it < n_rows * nchunk; it += nwarps) {
-    const int64_t i = it / nchunk;
-    const int chunk = (int)(it - i * nchunk);
-    const int c4 = chunk * 32 + lane;
-    if (c4 >= c4n) continue;
-    const int beg = rowptr[i], end = rowptr[i + 1];
-    const float den = (float)max(end - beg, 1);
-    const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + i * ldd)[c4], den);
+  // unit = (pair of consecutive rows, chunk); a warp's chunk is fixed (nwarps % nchunk == 0), its row pairs stride by
+  // nwarps / nchunk
+  const int chunk = (int)(warp0 % nchunk);
+  const int c4 = chunk * 32 + lane;
+  const int64_t pairs = (n_rows + 1) >> 1;
+  if (c4 < c4n) {
     const uint8_t* __restrict__ mrow = mask + c4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int k = beg; k < end; ++k) {
-      const unsigned m = __ldg(mrow + (int64_t)k * c4n);
-      acc.x += (m & 1u) ? d.x : 0.f;
-      acc.y += (m & 2u) ? d.y : 0.f;
-      acc.z += (m & 4u) ? d.z : 0.f;
-      acc.w += (m & 8u) ? d.w : 0.f;
+    for (int64_t pr = warp0 / nchunk; pr < pairs; pr += nwarps / nchunk) {
+      const int64_t i0 = 2 * pr, i1 = i0 + 1;
+      const bool two = i1 < n_rows;
+      const int b0 = rowptr[i0], e0 = rowptr[i0 + 1];
+      const int e1 = two ? rowptr[i1 + 1] : e0;
+      float4 d0 = reinterpret_cast<const float4*>(dhid + i0 * ldd)[c4];
+      float4 d1 = two ? reinterpret_cast<const float4*>(dhid + i1 * ldd)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      d0 = f4_div(d0, (float)max(e0 - b0, 1));
+      d1 = f4_div(d1, (float)max(e1 - e0, 1));
+      const float4 a0 = masked_count_sum(mrow, c4n, b0, e0, d0);
+      const float4 a1 = masked_count_sum(mrow, c4n, e0, e1, d1);
+      split_store4(a0, scale, hi + i0 * ldp + 4 * c4, lo != nullptr ? lo + i0 * ldp + 4 * c4 : nullptr);
+      if (two) split_store4(a1, scale, hi + i1 * ldp + 4 * c4, lo != nullptr ? lo + i1 * ldp + 4 * c4 : nullptr);
+      if (COLSUM) csum = f4_add(f4_add(csum, a0), a1);
     }
-    split_store4(acc, scale, hi + i * ldp + 4 * c4, lo != nullptr ? lo + i * ldp + 4 * c4 : nullptr);
-    if (COLSUM) csum = f4_add(csum, acc);
   }
   if (COLSUM) {
     const int w = threadIdx.x >> 5;
     csm[w][lane] = csum;
     __syncthreads();
     for (int idx = threadIdx.x; idx < c4n; idx += kAggThreads) {
-      const int chunk = idx >> 5, l = idx & 31;
+      const int ch = idx >> 5, l = idx & 31;
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int ww = 0; ww < kWarpsPerCta; ++ww)      // warps of this CTA that work on `chunk`, in warp order
-        if ((int)(((int64_t)blockIdx.x * kWarpsPerCta + ww) % nchunk) == chunk) t = f4_add(t, csm[ww][l]);
+      for (int ww = 0; ww < kWarpsPerCta; ++ww)      // warps of this CTA that work on chunk `ch`, in warp order
+        if ((int)(((int64_t)blockIdx.x * kWarpsPerCta + ww) % nchunk) == ch) t = f4_add(t, csm[ww][l]);
       reinterpret_cast<float4*>(colpart + (int64_t)blockIdx.x * hidden)[idx] = t;
     }
   }
@@ -754,32 +778,20 @@ extern "C" int stinet_csr_dq_factor(const int32_t* rowptr_t, const int32_t* rowp
   return check_launch("csr_dq_factor");
 }
 
+// grid of the target kernel: one warp per (row pair, 128-channel chunk), at most 4 waves, a multiple of the chunk count
+// (so the warp count is one too and a warp keeps its chunk for its whole row loop)
+static int edge_bwd_target_grid(int64_t n_rows, int64_t hidden) {
+  const int nchunk = (int)ceil_div(hidden >> 2, 32);
+  int g = wave_grid(((n_rows > 0 ? n_rows : 1) + 1) / 2 * nchunk, kWarpsPerCta, 8, 4);
+  return (int)(ceil_div(g, nchunk) * nchunk);      // 8 * g warps, a multiple of the chunk count
+}
 static size_t edge_bwd_colsum_bytes(int64_t n_rows, int64_t hidden) {
-  int gc = wave_grid((n_rows > 0 ? n_rows : 1) * ceil_div(hidden >> 2, 32), kWarpsPerCta, 8, 1);
-  gc += gc & 1;
-  return sizeof(float) * (size_t)gc * (size_t)hidden;
+  const int g = edge_bwd_target_grid(n_rows, hidden);
+  return sizeof(float) * ((size_t)g * (size_t)hidden + colsum_part_floats(g, hidden));
 }
 extern "C" size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden) {
   if (n_rows < 0 || hidden <= 0) return 0;
   return edge_bwd_colsum_bytes(n_rows, hidden);
-}
-
-// out[n] = sum over the rows of part[rows][N], 32 column lanes x 32 row lanes, fixed-order tree over the lanes
-__global__ void __launch_bounds__(1024) colsum_rows_kernel(const float* __restrict__ part, int rows, int N, float* __restrict__ out) {
-  __shared__ float sm[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + tx;
-  float t = 0.f;
-  if (n < N)
-    for (int c = ty; c < rows; c += 32) t += part[(int64_t)c * N + n];
-  sm[ty][tx] = t;
-  __syncthreads();
-  if (ty == 0 && n < N) {
-    float r = 0.f;
-#pragma unroll
-    for (int y = 0; y < 32; ++y) r += sm[y][tx];
-    out[n] = r;
-  }
 }
 
 static bool planes_ok(int64_t hidden, const void* hi, const void* lo, int64_t ld) {
@@ -822,21 +834,20 @@ extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, co
   const unsigned* am = reinterpret_cast<const unsigned*>(dhid_amax);
   __half* hi = static_cast<__half*>(dpq_hi);
   __half* lo = static_cast<__half*>(dpq_lo);
+  const int gt = edge_bwd_target_grid(n_rows, hidden);
   if (dp_colsum != nullptr) {
-    // dbias of the hoisted first Linear = column sums of dP: per-CTA partials from the target kernel, then one fixed-order
-    // reduction.  One wave of CTAs (full occupancy; a partial row per CTA), an even count (see the kernel's chunk rule).
-    int gc = wave_grid(n_rows * ceil_div(hidden >> 2, 32), kWarpsPerCta, 8, 1);
-    gc += gc & 1;
+    // dbias of the hoisted first Linear = column sums of dP: per-CTA partials from the target kernel, then the
+    // deterministic two-stage column sum over the partial rows
     const size_t need = edge_bwd_colsum_bytes(n_rows, hidden);
     STINET_REQUIRE(workspace && workspace_bytes >= need, STINET_ERR_WORKSPACE, "edge_message_bwd_planes: workspace %zu < %zu",
                    workspace_bytes, need);
     float* part = static_cast<float*>(workspace);
-    K(edge_message_bwd_target_planes_kernel<true><<<gc, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
+    K(edge_message_bwd_target_planes_kernel<true><<<gt, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
                                                                             n_rows, (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp, part));
-    K(colsum_rows_kernel<<<(unsigned)ceil_div(hidden, 32), 1024, 0, s>>>(part, gc, (int)hidden, dp_colsum));
+    run_colsum(part, hidden, nullptr, gt, hidden, dp_colsum, part + (size_t)gt * hidden, s);
   } else {
-    K(edge_message_bwd_target_planes_kernel<false><<<g, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
-                                                                            n_rows, (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp, nullptr));
+    K(edge_message_bwd_target_planes_kernel<false><<<gt, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
+                                                                             n_rows, (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp, nullptr));
   }
   if (n_rows > 0)
     K(edge_message_bwd_source_planes_kernel<<<g, kAggThreads, 0, s>>>(

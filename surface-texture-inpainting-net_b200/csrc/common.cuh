@@ -35,6 +35,12 @@ inline int check_launch(const char* what) {
     }                                    \
   } while (0)
 
+// deterministic two-stage masked column sums of a row-major fp32 matrix (gemm.cu): out[n] = sum_m x[m,n] * (rowmask ?
+// rowmask[m] > 0 : 1); `part` holds colsum_part_floats(M, N) floats
+void run_colsum(const float* x, int64_t ldx, const int32_t* rowmask, int64_t M, int64_t N, float* out, float* part,
+                cudaStream_t s);
+size_t colsum_part_floats(int64_t M, int64_t N);
+
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     part[(int64_t)blockIdx.y * N + n0] = t;
   }
 }
+size_t colsum_part_floats(int64_t M, int64_t N);
 // rows per stage-1 chunk: 512 for tall matrices, fewer (down to 32) when that is needed to put ~4 CTAs on every SM
 static int colsum_rows(int64_t M, int64_t N) {
   const int64_t col_ctas = ceil_div(N, 128);
@@ -311,9 +312,14 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
 }
 
 
+size_t colsum_part_floats(int64_t M, int64_t N) {
+  const int64_t rows = M > 0 ? M : 1;
+  return (size_t)ceil_div(rows, colsum_rows(rows, N)) * (size_t)N;
+}
+
 // masked column sums of dC [M,N] (dbias): two deterministic stages, partials in `part`
-static void run_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int64_t M, int64_t N, float* dbias,
-                       float* part, cudaStream_t s) {
+void run_colsum(const float* dC, int64_t ldc, const int32_t* rowmask, int64_t M, int64_t N, float* dbias,
+                float* part, cudaStream_t s) {
   const int rpc = colsum_rows(M > 0 ? M : 1, N);
   const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
   const bool vec = !(N & 3) && !(ldc & 3) && aligned16(dC);

@@ -214,6 +214,11 @@ struct Cfg {
   static constexpr bool kPre = MODE == MODE_BF16X3 || MODE == MODE_TF32X3P || MODE == MODE_F16X3;  // split done by the caller in HBM
   static constexpr bool kFp32 = MODE == MODE_TF32X3 || MODE == MODE_TF32X3P || MODE == MODE_F16X3; // fp32-class result: promotion + correction accumulator
   static constexpr bool kSplit = kConv || kPre;                    // stage holds hi and lo tiles, three MMAs per k-step
+  // F16X3: the B planes sit back to back in the stage ([A_hi][A_lo][B_hi][B_lo]) and the main / correction accumulators
+  // back to back in TMEM, so ONE MMA of width 2*BN evaluates A_hi * [B_hi ; B_lo]^T = [hi*hi | hi*lo] and a second one
+  // adds A_lo * B_hi^T to the correction half: A_hi is read from shared memory once instead of twice per k-step
+  // (20 KB instead of 24 KB of operand reads -- the kernel is shared-memory-bandwidth bound)
+  static constexpr bool kStacked = MODE == MODE_F16X3 && BN <= 128;
   static constexpr int kElemBytes = kBf16 ? 2 : 4;
   static constexpr int BKE = kRowBytes / kElemBytes;  // reduction elements per stage: 32 fp32 / 64 bf16
   static constexpr int MNE = kRowBytes / kElemBytes;  // MN elements per swizzle row of an MN-major operand
@@ -314,8 +319,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int plane = 0; plane < (C_::kPre ? 2 : 1); ++plane) {
             const CUtensorMap* mA = plane ? &tmA2 : &tmA;
             const CUtensorMap* mB = plane ? &tmB2 : &tmB;
-            const uint32_t a_dst = base + s * C_::kStageBytes + plane * C_::kLoadBytes;
-            const uint32_t b_dst = a_dst + C_::kABytes;
+            const uint32_t a_dst = C_::kStacked ? base + s * C_::kStageBytes + plane * C_::kABytes
+                                                : base + s * C_::kStageBytes + plane * C_::kLoadBytes;
+            const uint32_t b_dst = C_::kStacked ? base + s * C_::kStageBytes + 2 * C_::kABytes + plane * C_::kBBytes
+                                                : a_dst + C_::kABytes;
             if (!A_MN) {
               tma_load_2d(a_dst, mA, t0, w.i0, full_bar(s));
             } else {
@@ -343,6 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t fmt = C_::kF16 ? 0u : (kBf16 ? 1u : 2u);   // operand format: f16 / bf16 / tf32
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * BN) >> 3) << 17);   // the stacked MMA: N = 2 * BN
       // per-operand descriptor geometry
       constexpr uint32_t kMnAtomStride = C_::BKE * kRowBytes;              // bytes between MN atoms (one TMA box)
       constexpr uint32_t kMnLayout = kBf16 ? kLayoutSW128 : kLayoutSW128Base32;
@@ -365,13 +373,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           { DBG_T0(); mbar_wait(tempty_bar(buf), aph ^ 1u); DBG_ADD(3); }  // the epilogue has drained this accumulator buffer
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + buf * BN;
-          const uint32_t tmem_s = g.split_acc ? tmem_d + 2 * BN : tmem_d;   // correction-term accumulator
+          const uint32_t tmem_d = C_::kStacked ? tmem_base + buf * 2 * BN : tmem_base + buf * BN;
+          // correction-term accumulator: right behind the main one (stacked) or in the upper half of the allocation
+          const uint32_t tmem_s = C_::kStacked ? tmem_d + BN : (g.split_acc ? tmem_d + 2 * BN : tmem_d);
           for (int kb = kb0; kb < kb1; ++kb) {
             { DBG_T0(); mbar_wait(C_::kConv ? conv_bar(s) : full_bar(s), ph); DBG_ADD(2); }
             tcgen05_fence_after();
             const uint32_t a_hi = base + s * C_::kStageBytes;
-            const uint32_t b_hi = a_hi + C_::kABytes;
+            const uint32_t b_hi = C_::kStacked ? a_hi + 2 * C_::kABytes : a_hi + C_::kABytes;
 #pragma unroll
             for (int k = 0; k < C_::BKE / C_::UMMA_K; ++k) {
               const uint32_t a_off = A_MN ? k * kMnKStep : k * 32u;
@@ -385,7 +394,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             : make_smem_desc(addr + b_off, 16u, 1024u, kLayoutSW128);
               };
               const uint32_t accumulate = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (C_::kSplit) {
+              if (C_::kStacked) {
+                const uint32_t a_lo = a_hi + C_::kABytes;
+                umma<kBf16>(tmem_d, adesc(a_hi), bdesc(b_hi), idesc2, accumulate);   // [hi*hi | hi*lo] -> [main | corr]
+                umma<kBf16>(tmem_s, adesc(a_lo), bdesc(b_hi), idesc, 1u);            // lo*hi -> corr
+              } else if (C_::kSplit) {
                 const uint32_t a_lo = a_hi + C_::kLoadBytes, b_lo = b_hi + C_::kLoadBytes;
                 umma<kBf16>(tmem_s, adesc(a_lo), bdesc(b_hi), idesc, accumulate);
                 umma<kBf16>(tmem_s, adesc(a_hi), bdesc(b_lo), idesc, 1u);
@@ -473,14 +486,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
         { DBG_T0(); mbar_wait(tfull_bar(buf), aph); DBG_ADD(4); }
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)(h * EC);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (C_::kStacked ? 2 * BN : BN) + (uint32_t)(h * EC);
 #pragma unroll
         for (int cc = 0; cc < EC; cc += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + cc, r);
           if (C_::kFp32 && g.split_acc) {
             uint32_t r2[32];
-            tmem_ld32(taddr + 2 * BN + cc, r2);
+            tmem_ld32(taddr + (C_::kStacked ? BN : 2 * BN) + cc, r2);
 #pragma unroll
             for (int c = 0; c < 32; ++c)   // F16X3: the lo planes carry a factor 2^11
               r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r2[c]) * (C_::kF16 ? (1.f / 2048.f) : 1.f));

@@ -379,6 +379,68 @@ def test_edge_message_mask_kernels_equal_recomputing_kernels(kind, h):
     assert torch.equal(d0, d1)
 
 
+@pytest.mark.parametrize("kind", ["ico", "graph18_isolated", "dilated_asym", "multi_edges", "empty"])
+@pytest.mark.parametrize("h", [4, 64, 128, 320, 2048])
+def test_edge_message_plane_kernels_equal_the_fp32_kernels(kind, h):
+    """The message-stage kernels that write fp16 operand planes (hid in forward, dPQ in backward, scales from the
+    bounds 2 max|PQ| and max|dhid| * dq_factor) against the fp32 mask kernels: the planes reproduce the fp32 values to
+    22 significand bits of the bound, the decision masks are identical, the bounds hold, and the bias gradient that the
+    target kernel accumulates on the side equals the column sums of dP."""
+    from stinet_b200 import _abi, ops
+    from stinet_b200.graph import EdgeCSR, _stream
+    ei, n = _graph(kind)
+    csr = EdgeCSR(ei.to(DEV), n)
+    rs, cs, es = csr.by_source()
+    g = torch.Generator().manual_seed(23 + h)
+    pq = (torch.randn(n, 2 * h, generator=g) * 3).to(DEV)
+    dh = (torch.randn(n, h, generator=g) * 1e-6).to(DEV)                      # gradient-sized values: the scale matters
+    P, Q, ld = pq.data_ptr(), pq.data_ptr() + 4 * h, 2 * h
+    s = _stream()
+    hid = torch.empty(n, h, device=DEV)
+    mask0 = torch.zeros(max(csr.e, 1), h // 4, dtype=torch.uint8, device=DEV)
+    mask1 = torch.zeros_like(mask0)
+    _abi.call("stinet_edge_message_fwd_mask", P, ld, Q, ld, csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h,
+              hid.data_ptr(), h, mask0.data_ptr(), s)
+    pq_amax = pq.abs().max().reshape(1)
+    hp = ops._new_planes(n, h, True, DEV)
+    _abi.call("stinet_edge_message_fwd_planes", P, ld, Q, ld, csr.rowptr_t.data_ptr(), csr.col_t.data_ptr(), n, h,
+              pq_amax.data_ptr(), hp.hi.data_ptr(), hp.lo.data_ptr(), hp.ld, hp.exp.data_ptr(), mask1.data_ptr(), s)
+    assert torch.equal(mask0, mask1)
+
+    def value(p, cols):
+        return (p.hi[:, :cols].double() + p.lo[:, :cols].double() / 2048.0) * 2.0 ** int(p.exp.item())
+
+    bound = 2.0 * float(pq_amax)
+    assert float(hid.abs().max()) <= bound
+    assert float((value(hp, h) - hid.double()).abs().max()) <= bound * 2.0 ** -21
+    # backward
+    d_ref = torch.empty(n, 2 * h, device=DEV)
+    tpos = csr.tpos_s()
+    _abi.call("stinet_edge_message_bwd_target_mask", dh.data_ptr(), h, csr.rowptr_t.data_ptr(), mask0.data_ptr(), n, h,
+              d_ref.data_ptr(), 2 * h, s)
+    _abi.call("stinet_edge_message_bwd_source_mask", dh.data_ptr(), h, csr.rowptr_t.data_ptr(), rs.data_ptr(),
+              cs.data_ptr(), tpos.data_ptr(), mask0.data_ptr(), n, h, d_ref.data_ptr() + 4 * h, 2 * h, s)
+    dh_amax = dh.abs().max().reshape(1)
+    dp = ops._new_planes(n, 2 * h, True, DEV)
+    db = torch.full((h,), float("nan"), device=DEV)
+    nb = _abi.query("stinet_edge_message_bwd_workspace_bytes", n, h)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
+    _abi.call("stinet_edge_message_bwd_planes", dh.data_ptr(), h, dh_amax.data_ptr(), csr.dq_factor().data_ptr(),
+              csr.rowptr_t.data_ptr(), rs.data_ptr(), cs.data_ptr(), tpos.data_ptr(), mask0.data_ptr(), n, h,
+              dp.hi.data_ptr(), dp.lo.data_ptr(), dp.ld, dp.exp.data_ptr(), db.data_ptr(), ws.data_ptr(), nb, s)
+    dbound = float(dh_amax) * max(1.0, float(csr.dq_factor()))
+    assert float(d_ref.abs().max()) <= dbound * (1 + 1e-6)
+    assert float((value(dp, 2 * h) - d_ref.double()).abs().max()) <= dbound * 2.0 ** -21
+    ref_db = d_ref[:, :h].double().sum(0)
+    assert float((db.double() - ref_db).abs().max()) <= 1e-5 * max(float(ref_db.abs().max()), 1e-30) + 1e-12 * dbound
+    # without the bias gradient (no workspace): same planes
+    dp2 = ops._new_planes(n, 2 * h, True, DEV)
+    _abi.call("stinet_edge_message_bwd_planes", dh.data_ptr(), h, dh_amax.data_ptr(), csr.dq_factor().data_ptr(),
+              csr.rowptr_t.data_ptr(), rs.data_ptr(), cs.data_ptr(), tpos.data_ptr(), mask0.data_ptr(), n, h,
+              dp2.hi.data_ptr(), dp2.lo.data_ptr(), dp2.ld, dp2.exp.data_ptr(), None, None, 0, s)
+    assert torch.equal(dp.hi, dp2.hi) and torch.equal(dp.lo, dp2.lo) and torch.equal(dp.exp, dp2.exp)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # affine segmented norms (SURVEY 8a row a10) and the in-place skip concatenation of the unpool kernel (row a8)
 
