@@ -309,13 +309,15 @@ int stinet_edge_message_fwd_planes(const float* P, int64_t ldp, const float* Q, 
                                    const int32_t* col_t, int64_t n_rows, int64_t hidden, const float* pq_amax,
                                    void* hid_hi, void* hid_lo, int64_t ldh, int32_t* hid_exp, void* mask,
                                    stinet_stream_t stream);
-int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* dhid_amax, const float* dq_factor,
+int stinet_edge_message_bwd_planes(float* dhid, int64_t ldd, const float* dhid_amax, const float* dq_factor,
                                    const int32_t* rowptr_t, const int32_t* rowptr_s, const int32_t* col_s,
                                    const int32_t* tpos_s, const void* mask, int64_t n_rows, int64_t hidden, void* dpq_hi,
                                    void* dpq_lo, int64_t ldp, int32_t* dpq_exp, float* dp_colsum, void* workspace,
                                    size_t workspace_bytes, stinet_stream_t stream);
 /* dp_colsum (nullable, float[hidden]): also sum_i dP[i,:], the bias gradient of the hoisted first Linear, accumulated by the
- * kernel that produces dP (per-CTA partials in `workspace`, fixed-order second stage). */
+ * kernel that produces dP (per-CTA partials in `workspace`, fixed-order second stage; for hidden > 256 taken from the finished
+ * planes instead).  dhid is CONSUMED: its rows are overwritten with dhid[i,:] / deg_i on the way (the second kernel gathers the
+ * scaled rows once per out-edge). */
 size_t stinet_edge_message_bwd_workspace_bytes(int64_t n_rows, int64_t hidden);
 
 /* ---- operand planes of ALL dense-layer weights of a network in two launches (per step: weights change with every optimizer

@@ -421,26 +421,23 @@ edge_message_fwd_planes_kernel(const float* __restrict__ P, int64_t ldp, const f
     const float4 p = reinterpret_cast<const float4*>(P + i * ldp)[c4];
     uint8_t* __restrict__ mrow = mask + c4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int k = beg;
-    for (; k + 4 <= end; k += 4) {
-      int j[4];
-      float4 q[4];
+    // up to eight neighbour rows in flight per lane (a mesh vertex has ~6 in-edges: one batch), accumulated in edge order
+    for (int k0 = beg; k0 < end; k0 += 8) {
+      int j[8];
+      float4 q[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) j[u] = col[k + u];
+      for (int u = 0; u < 8; ++u) j[u] = (k0 + u < end) ? col[k0 + u] : -1;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) q[u] = reinterpret_cast<const float4*>(Q + (int64_t)j[u] * ldq)[c4];
+      for (int u = 0; u < 8; ++u)
+        q[u] = j[u] >= 0 ? reinterpret_cast<const float4*>(Q + (int64_t)j[u] * ldq)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float sx = p.x + q[u].x, sy = p.y + q[u].y, sz = p.z + q[u].z, sw = p.w + q[u].w;
-        acc.x += relu(sx); acc.y += relu(sy); acc.z += relu(sz); acc.w += relu(sw);
-        if (MASK) mrow[(int64_t)(k + u) * c4n] = (uint8_t)nibble(sx, sy, sz, sw);
+      for (int u = 0; u < 8; ++u) {
+        if (k0 + u < end) {
+          const float sx = p.x + q[u].x, sy = p.y + q[u].y, sz = p.z + q[u].z, sw = p.w + q[u].w;
+          acc.x += relu(sx); acc.y += relu(sy); acc.z += relu(sz); acc.w += relu(sw);
+          if (MASK) mrow[(int64_t)(k0 + u) * c4n] = (uint8_t)nibble(sx, sy, sz, sw);
+        }
       }
-    }
-    for (; k < end; ++k) {
-      const float4 q = reinterpret_cast<const float4*>(Q + (int64_t)col[k] * ldq)[c4];
-      const float sx = p.x + q.x, sy = p.y + q.y, sz = p.z + q.z, sw = p.w + q.w;
-      acc.x += relu(sx); acc.y += relu(sy); acc.z += relu(sz); acc.w += relu(sw);
-      if (MASK) mrow[(int64_t)k * c4n] = (uint8_t)nibble(sx, sy, sz, sw);
     }
     split_store4(f4_div(acc, den), scale, hi + i * ldh + 4 * c4, lo != nullptr ? lo + i * ldh + 4 * c4 : nullptr);
   }
@@ -478,11 +475,13 @@ __device__ __forceinline__ float4 masked_count_sum(const uint8_t* __restrict__ m
 
 template <bool COLSUM>
 __global__ void __launch_bounds__(kAggThreads)
-edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr,
+edge_message_bwd_target_planes_kernel(float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr,
                                       const uint8_t* __restrict__ mask, int64_t n_rows, int hidden,
                                       const unsigned* __restrict__ dhid_amax, const float* __restrict__ dq_factor,
                                       __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp,
                                       int32_t* __restrict__ exp_out, float* __restrict__ colpart) {
+  // dhid[i,:] is overwritten with dhid[i,:] / deg_i: the source kernel that runs next gathers these rows once per
+  // out-edge and would otherwise repeat the division (and two row-pointer loads) per edge
   __shared__ float4 csm[COLSUM ? kWarpsPerCta : 1][32];
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
   const int sft = dpq_shift(dhid_amax, dq_factor);
@@ -509,6 +508,8 @@ edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ld
       float4 d1 = two ? reinterpret_cast<const float4*>(dhid + i1 * ldd)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
       d0 = f4_div(d0, (float)max(e0 - b0, 1));
       d1 = f4_div(d1, (float)max(e1 - e0, 1));
+      reinterpret_cast<float4*>(dhid + i0 * ldd)[c4] = d0;
+      if (two) reinterpret_cast<float4*>(dhid + i1 * ldd)[c4] = d1;
       const float4 a0 = masked_count_sum(mrow, c4n, b0, e0, d0);
       const float4 a1 = masked_count_sum(mrow, c4n, e0, e1, d1);
       split_store4(a0, scale, hi + i0 * ldp + 4 * c4, lo != nullptr ? lo + i0 * ldp + 4 * c4 : nullptr);
@@ -531,13 +532,14 @@ edge_message_bwd_target_planes_kernel(const float* __restrict__ dhid, int64_t ld
   }
 }
 
+// dQ[j,:] = sum over out-edges (j -> i) of ds[i,:] * bit, ds = dhid / deg (left behind by the target kernel): one gathered
+// row and one mask byte per out-edge and column; four out-edges' indices, rows and masks in flight per lane
 __global__ void __launch_bounds__(kAggThreads)
-edge_message_bwd_source_planes_kernel(const float* __restrict__ dhid, int64_t ldd, const int32_t* __restrict__ rowptr_t,
-                                      const int32_t* __restrict__ rowptr_s, const int32_t* __restrict__ col_s,
-                                      const int32_t* __restrict__ tpos_s, const uint8_t* __restrict__ mask,
-                                      int64_t n_rows, int hidden, const unsigned* __restrict__ dhid_amax,
-                                      const float* __restrict__ dq_factor, __half* __restrict__ hi,
-                                      __half* __restrict__ lo, int64_t ldp) {
+edge_message_bwd_source_planes_kernel(const float* __restrict__ ds, int64_t ldd, const int32_t* __restrict__ rowptr_s,
+                                      const int32_t* __restrict__ col_s, const int32_t* __restrict__ tpos_s,
+                                      const uint8_t* __restrict__ mask, int64_t n_rows, int hidden,
+                                      const unsigned* __restrict__ dhid_amax, const float* __restrict__ dq_factor,
+                                      __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldp) {
   const float scale = plane_scale(dpq_shift(dhid_amax, dq_factor));
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -552,16 +554,30 @@ edge_message_bwd_source_planes_kernel(const float* __restrict__ dhid, int64_t ld
     const int beg = rowptr_s[j], end = rowptr_s[j + 1];
     const uint8_t* __restrict__ mrow = mask + c4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int k = beg; k < end; ++k) {
-      const int i = col_s[k];
-      const float den = (float)max(rowptr_t[i + 1] - rowptr_t[i], 1);
-      const unsigned m = __ldg(mrow + (int64_t)tpos_s[k] * c4n);
-      const float4 d = f4_div(reinterpret_cast<const float4*>(dhid + (int64_t)i * ldd)[c4], den);
-      acc.x += (m & 1u) ? d.x : 0.f;
-      acc.y += (m & 2u) ? d.y : 0.f;
-      acc.z += (m & 4u) ? d.z : 0.f;
-      acc.w += (m & 8u) ? d.w : 0.f;
+    for (int k0 = beg; k0 < end; k0 += 8) {
+      int i[8], t[8];
+      unsigned m[8];
+      float4 d[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool on = k0 + u < end;
+        i[u] = on ? col_s[k0 + u] : -1;
+        t[u] = on ? tpos_s[k0 + u] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        m[u] = i[u] >= 0 ? (unsigned)__ldg(mrow + (int64_t)t[u] * c4n) : 0u;
+        d[u] = i[u] >= 0 ? reinterpret_cast<const float4*>(ds + (int64_t)i[u] * ldd)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (i[u] >= 0) {
+          acc.x += (m[u] & 1u) ? d[u].x : 0.f;
+          acc.y += (m[u] & 2u) ? d[u].y : 0.f;
+          acc.z += (m[u] & 4u) ? d[u].z : 0.f;
+          acc.w += (m[u] & 8u) ? d[u].w : 0.f;
+        }
+      }
     }
     split_store4(acc, scale, hi + j * ldp + 4 * c4, lo != nullptr ? lo + j * ldp + 4 * c4 : nullptr);
   }
@@ -785,7 +801,9 @@ static int edge_bwd_target_grid(int64_t n_rows, int64_t hidden) {
   int g = wave_grid(((n_rows > 0 ? n_rows : 1) + 1) / 2 * nchunk, kWarpsPerCta, 8, 4);
   return (int)(ceil_div(g, nchunk) * nchunk);      // 8 * g warps, a multiple of the chunk count
 }
+static bool edge_bwd_fused_colsum(int64_t hidden) { return hidden <= 256; }
 static size_t edge_bwd_colsum_bytes(int64_t n_rows, int64_t hidden) {
+  if (!edge_bwd_fused_colsum(hidden)) return sizeof(float) * colsum_part_floats(n_rows, hidden);
   const int g = edge_bwd_target_grid(n_rows, hidden);
   return sizeof(float) * ((size_t)g * (size_t)hidden + colsum_part_floats(g, hidden));
 }
@@ -818,7 +836,7 @@ extern "C" int stinet_edge_message_fwd_planes(const float* P, int64_t ldp, const
   return check_launch("edge_message_fwd_planes");
 }
 
-extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, const float* dhid_amax,
+extern "C" int stinet_edge_message_bwd_planes(float* dhid, int64_t ldd, const float* dhid_amax,
                                               const float* dq_factor, const int32_t* rowptr_t,
                                               const int32_t* rowptr_s, const int32_t* col_s, const int32_t* tpos_s,
                                               const void* mask, int64_t n_rows, int64_t hidden, void* dpq_hi,
@@ -835,7 +853,16 @@ extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, co
   __half* hi = static_cast<__half*>(dpq_hi);
   __half* lo = static_cast<__half*>(dpq_lo);
   const int gt = edge_bwd_target_grid(n_rows, hidden);
-  if (dp_colsum != nullptr) {
+  if (dp_colsum != nullptr && !edge_bwd_fused_colsum(hidden)) {
+    // wide rows (coarse levels: few rows, thousands of channels): a partial row per CTA would outweigh the data itself;
+    // the column sums are taken from the finished dP planes instead
+    const size_t need = edge_bwd_colsum_bytes(n_rows, hidden);
+    STINET_REQUIRE(workspace && workspace_bytes >= need, STINET_ERR_WORKSPACE, "edge_message_bwd_planes: workspace %zu < %zu",
+                   workspace_bytes, need);
+    K(edge_message_bwd_target_planes_kernel<false><<<gt, kAggThreads, 0, s>>>(dhid, ldd, rowptr_t, static_cast<const uint8_t*>(mask),
+                                                                             n_rows, (int)hidden, am, dq_factor, hi, lo, ldp, dpq_exp, nullptr));
+    run_colsum_planes(hi, lo, ldp, dpq_exp, n_rows, hidden, dp_colsum, static_cast<float*>(workspace), s);
+  } else if (dp_colsum != nullptr) {
     // dbias of the hoisted first Linear = column sums of dP: per-CTA partials from the target kernel, then the
     // deterministic two-stage column sum over the partial rows
     const size_t need = edge_bwd_colsum_bytes(n_rows, hidden);
@@ -851,7 +878,7 @@ extern "C" int stinet_edge_message_bwd_planes(const float* dhid, int64_t ldd, co
   }
   if (n_rows > 0)
     K(edge_message_bwd_source_planes_kernel<<<g, kAggThreads, 0, s>>>(
-        dhid, ldd, rowptr_t, rowptr_s, col_s, tpos_s, static_cast<const uint8_t*>(mask), n_rows, (int)hidden, am, dq_factor,
+        dhid, ldd, rowptr_s, col_s, tpos_s, static_cast<const uint8_t*>(mask), n_rows, (int)hidden, am, dq_factor,
         hi + hidden, lo != nullptr ? lo + hidden : nullptr, ldp));
   return check_launch("edge_message_bwd_planes");
 }

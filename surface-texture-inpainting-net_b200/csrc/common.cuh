@@ -40,6 +40,9 @@ inline int check_launch(const char* what) {
 void run_colsum(const float* x, int64_t ldx, const int32_t* rowmask, int64_t M, int64_t N, float* out, float* part,
                 cudaStream_t s);
 size_t colsum_part_floats(int64_t M, int64_t N);
+// the same over a matrix held as fp16 operand planes (hi + lo 2^-11) 2^exp
+void run_colsum_planes(const __half* hi, const __half* lo, int64_t ldp, const int32_t* exp, int64_t M, int64_t N, float* out,
+                       float* part, cudaStream_t s);
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 

@@ -325,6 +325,10 @@ extern "C" int stinet_csr_cross_positions(const int32_t* eid_t, const int32_t* e
   if (n_items == 0) return STINET_OK;
   STINET_REQUIRE(eid_t && eid_s && tpos_s && scratch, STINET_ERR_ARG, "csr_cross_positions: null pointer");
   const int grid = wave_grid(n_items, 256 * 4, 8);
+  // an edge that one of the two structures dropped (index out of range, status bit 0) has no by-target slot: it maps to
+  // slot 0 instead of whatever the scratch buffer held
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(int32_t) * (size_t)n_items, stream);
+  STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "csr_cross_positions: cudaMemsetAsync: %s", cudaGetErrorString(e));
   K(invert_perm_kernel<<<grid, 256, 0, stream>>>(eid_t, n_items, scratch));
   K(gather_i32_kernel<<<grid, 256, 0, stream>>>(scratch, eid_s, n_items, tpos_s));
   return check_launch("csr_cross_positions");

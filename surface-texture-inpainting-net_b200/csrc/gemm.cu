@@ -396,6 +396,16 @@ __global__ void __launch_bounds__(1024) colsum_planes_final_kernel(const float* 
   }
 }
 
+// out[n] = sum_m x[m,n] of a matrix held as operand planes; `part` holds colsum_part_floats(M, N) floats
+void run_colsum_planes(const __half* hi, const __half* lo, int64_t ldp, const int32_t* exp, int64_t M, int64_t N, float* out,
+                       float* part, cudaStream_t s) {
+  const int rpc = colsum_rows(M > 0 ? M : 1, N);
+  const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
+  dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
+  K(colsum_planes_partial_kernel<<<g2, 256, 0, s>>>(hi, lo, ldp, M, (int)N, rpc, part));
+  K(colsum_planes_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(part, chunks, (int)N, exp, out));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // operand planes for the fp16 tensor-core modes (see include/stinet_b200.h, "dense layers on operand PLANES")
 
@@ -1004,12 +1014,7 @@ extern "C" int stinet_colsum_planes(const void* hi, const void* lo, int64_t ldp,
   GemmWs w = carve_gemm(workspace, M, N, 1, STINET_PREC_FP32);
   STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "colsum_planes: workspace %zu < %zu",
                  workspace_bytes, w.bytes);
-  const int rpc = colsum_rows(M > 0 ? M : 1, N);
-  const int chunks = (int)ceil_div(M > 0 ? M : 1, rpc);
-  dim3 g2((unsigned)ceil_div(N, 128), (unsigned)chunks);
-  K(colsum_planes_partial_kernel<<<g2, 256, 0, s>>>(static_cast<const __half*>(hi), static_cast<const __half*>(lo), ldp, M, (int)N,
-                                                   rpc, w.colsum));
-  K(colsum_planes_final_kernel<<<(unsigned)ceil_div(N, 32), 1024, 0, s>>>(w.colsum, chunks, (int)N, exp, out));
+  run_colsum_planes(static_cast<const __half*>(hi), static_cast<const __half*>(lo), ldp, exp, M, N, out, w.colsum, s);
   return check_launch("colsum_planes");
 }
 

@@ -425,7 +425,8 @@ def test_edge_message_plane_kernels_equal_the_fp32_kernels(kind, h):
     db = torch.full((h,), float("nan"), device=DEV)
     nb = _abi.query("stinet_edge_message_bwd_workspace_bytes", n, h)
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=DEV)
-    _abi.call("stinet_edge_message_bwd_planes", dh.data_ptr(), h, dh_amax.data_ptr(), csr.dq_factor().data_ptr(),
+    dh1, dh2 = dh.clone(), dh.clone()                # the call consumes dhid (rows are rescaled by 1 / deg in place)
+    _abi.call("stinet_edge_message_bwd_planes", dh1.data_ptr(), h, dh_amax.data_ptr(), csr.dq_factor().data_ptr(),
               csr.rowptr_t.data_ptr(), rs.data_ptr(), cs.data_ptr(), tpos.data_ptr(), mask0.data_ptr(), n, h,
               dp.hi.data_ptr(), dp.lo.data_ptr(), dp.ld, dp.exp.data_ptr(), db.data_ptr(), ws.data_ptr(), nb, s)
     dbound = float(dh_amax) * max(1.0, float(csr.dq_factor()))
@@ -435,7 +436,7 @@ def test_edge_message_plane_kernels_equal_the_fp32_kernels(kind, h):
     assert float((db.double() - ref_db).abs().max()) <= 1e-5 * max(float(ref_db.abs().max()), 1e-30) + 1e-12 * dbound
     # without the bias gradient (no workspace): same planes
     dp2 = ops._new_planes(n, 2 * h, True, DEV)
-    _abi.call("stinet_edge_message_bwd_planes", dh.data_ptr(), h, dh_amax.data_ptr(), csr.dq_factor().data_ptr(),
+    _abi.call("stinet_edge_message_bwd_planes", dh2.data_ptr(), h, dh_amax.data_ptr(), csr.dq_factor().data_ptr(),
               csr.rowptr_t.data_ptr(), rs.data_ptr(), cs.data_ptr(), tpos.data_ptr(), mask0.data_ptr(), n, h,
               dp2.hi.data_ptr(), dp2.lo.data_ptr(), dp2.ld, dp2.exp.data_ptr(), None, None, 0, s)
     assert torch.equal(dp.hi, dp2.hi) and torch.equal(dp.lo, dp2.lo) and torch.equal(dp.exp, dp2.exp)
