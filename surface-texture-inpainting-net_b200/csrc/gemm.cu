@@ -285,11 +285,11 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
 }
 size_t colsum_part_floats(int64_t M, int64_t N);
-// rows per stage-1 chunk: 512 for tall matrices, fewer (down to 32) when that is needed to put ~4 CTAs on every SM
+// rows per stage-1 chunk: 512 for tall matrices, fewer (down to 32) when that is needed to put ~8 CTAs on every SM
 static int colsum_rows(int64_t M, int64_t N) {
   const int64_t col_ctas = ceil_div(N, 128);
   int r = 512;
-  while (r > 32 && col_ctas * ceil_div(M > 0 ? M : 1, r) < 4 * kSMs) r >>= 1;
+  while (r > 32 && col_ctas * ceil_div(M > 0 ? M : 1, r) < 8 * kSMs) r >>= 1;
   return r;
 }
 // stage 2: out[n] = sum_chunks partial[chunk][n]; 32 column lanes x 32 chunk lanes, fixed-order tree over the lanes

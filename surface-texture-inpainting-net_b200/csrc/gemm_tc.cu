@@ -479,6 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4* stage = reinterpret_cast<float4*>(base_ptr + staging_off + (size_t)ew * 4096);
     float acc[EC];
     uint32_t acc_it = 0;
+    unsigned amax_bits = 0u;           // max |C| over every tile of this warp, published once at the end
     DBG_DECL();
     for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
       const Unit w = decode(u);
@@ -525,7 +526,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < EC; ++c) acc[c] = acc[c] * f1 * f2;
       }
-      unsigned amax_bits = 0u;
       if (row0 < g.I) {
 #pragma unroll
         for (int cc = 0; cc < EC; cc += 32) {
@@ -549,12 +549,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) tma_store_3d(&tmC, smem_u32(stage), jb, row0, w.z);
         }
       }
-      if (g.amax_out != nullptr) {
-        // rows / columns outside the matrix hold exact zeros (TMA zero fill, no bias), so they cannot raise the maximum
-        amax_bits = __reduce_max_sync(0xFFFFFFFFu, amax_bits);
-        if (lane == 0 && amax_bits > *reinterpret_cast<volatile unsigned*>(g.amax_out)) atomicMax(g.amax_out, amax_bits);
-      }
       DBG_ADD(5);
+    }
+    if (g.amax_out != nullptr) {
+      // rows / columns outside the matrix hold exact zeros (TMA zero fill, no bias), so they cannot raise the maximum
+      amax_bits = __reduce_max_sync(0xFFFFFFFFu, amax_bits);
+      if (lane == 0 && amax_bits > *reinterpret_cast<volatile unsigned*>(g.amax_out)) atomicMax(g.amax_out, amax_bits);
     }
     if (lane == 0) bulk_wait_all();
     DBG_FLUSH(threadIdx.x == 32 * kEpiWarp0, 4, 5);

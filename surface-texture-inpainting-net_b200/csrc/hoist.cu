@@ -119,17 +119,45 @@ __device__ __forceinline__ void weight_values(const WeightEntry& e, int64_t r, i
   }
 }
 
+// four consecutive source elements per thread when the row width and the pitches allow 16-byte accesses
+__device__ __forceinline__ bool entry_vec(const WeightEntry& e) {
+  return (e.cols & 3) == 0 && (e.ldw & 3) == 0 && aligned16(e.w) && (e.kind != 1 || ((e.cols & 3) == 0));
+}
+__device__ __forceinline__ void weight_values4(const WeightEntry& e, int64_t r, int64_t c, float4& p, float4& q) {
+  const float4 a = *reinterpret_cast<const float4*>(e.w + r * e.ldw + c);
+  if (e.kind == 0) {
+    p = a;
+    q = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (e.kind == 1) {
+    q = *reinterpret_cast<const float4*>(e.w + r * e.ldw + e.cols + c);
+    p = make_float4(a.x - q.x, a.y - q.y, a.z - q.z, a.w - q.w);
+  } else {
+    q = a;
+    p = make_float4(-a.x, -a.y, -a.z, -a.w);
+  }
+}
+
 __global__ void __launch_bounds__(256) wplanes_amax_kernel(const WeightEntry* __restrict__ tab, int n_entries) {
   const int ei = find_entry(tab, n_entries, blockIdx.x);
   const WeightEntry e = tab[ei];
   const int64_t total = (int64_t)e.rows * e.cols;
   const int64_t base = (int64_t)(blockIdx.x - e.chunk0) * kWChunk;
+  const int64_t stop = min(total, base + kWChunk);
   unsigned m = 0u;
-  for (int64_t idx = base + threadIdx.x; idx < min(total, base + kWChunk); idx += 256) {
-    const int64_t r = idx / e.cols, c = idx - r * e.cols;
-    float p, q;
-    weight_values(e, r, c, p, q);
-    m = max(max(m, __float_as_uint(p) & 0x7FFFFFFFu), __float_as_uint(q) & 0x7FFFFFFFu);
+  if (entry_vec(e)) {
+    for (int64_t idx = base + 4 * threadIdx.x; idx < stop; idx += 4 * 256) {
+      const int64_t r = idx / e.cols, c = idx - r * e.cols;
+      float4 p, q;
+      weight_values4(e, r, c, p, q);
+      m = amax4(amax4(m, p), q);
+    }
+  } else {
+    for (int64_t idx = base + threadIdx.x; idx < stop; idx += 256) {
+      const int64_t r = idx / e.cols, c = idx - r * e.cols;
+      float p, q;
+      weight_values(e, r, c, p, q);
+      m = max(max(m, __float_as_uint(p) & 0x7FFFFFFFu), __float_as_uint(q) & 0x7FFFFFFFu);
+    }
   }
   amax_publish(m, e.amax);
 }
@@ -139,10 +167,27 @@ __global__ void __launch_bounds__(256) wplanes_split_kernel(const WeightEntry* _
   const WeightEntry e = tab[ei];
   const int64_t total = (int64_t)e.rows * e.cols;
   const int64_t base = (int64_t)(blockIdx.x - e.chunk0) * kWChunk;
+  const int64_t stop = min(total, base + kWChunk);
   const int sft = plane_shift(*e.amax);
   const float scale = plane_scale(sft);
   if (blockIdx.x == e.chunk0 && threadIdx.x == 0) *e.exp = -sft;
-  for (int64_t idx = base + threadIdx.x; idx < min(total, base + kWChunk); idx += 256) {
+  if (entry_vec(e)) {                                  // ldp is a multiple of 8: 8-byte plane stores are aligned
+    for (int64_t idx = base + 4 * threadIdx.x; idx < stop; idx += 4 * 256) {
+      const int64_t r = idx / e.cols, c = idx - r * e.cols;
+      float4 p, q;
+      weight_values4(e, r, c, p, q);
+      split_store4(p, scale, e.hi + r * e.ldp + c, e.lo ? e.lo + r * e.ldp + c : nullptr);
+      if (e.kind != 0) {
+        split_store4(q, scale, e.hi + (r + e.rows) * e.ldp + c, e.lo ? e.lo + (r + e.rows) * e.ldp + c : nullptr);
+        if (e.bcat && c == 0) {
+          e.bcat[r] = e.b ? e.b[r] : 0.f;
+          e.bcat[e.rows + r] = 0.f;
+        }
+      }
+    }
+    return;
+  }
+  for (int64_t idx = base + threadIdx.x; idx < stop; idx += 256) {
     const int64_t r = idx / e.cols, c = idx - r * e.cols;
     float p, q;
     weight_values(e, r, c, p, q);
