@@ -18,6 +18,7 @@ The dense Conv2d half of the file (Resnet2D, :18-76, :524-659) is out of scope (
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -29,6 +30,9 @@ from ..graph import GraphCache, Segments
 from .modules import edge_conv_filter, edge_conv_translation_invariance, sage_conv_filter
 from .modules.fastinstancenorm import FastInstanceNorm
 from .modules.singlebatchgroupnorm import SingleBatchGraphNorm
+
+
+_NVTX = os.environ.get("STINET_NVTX", "0") == "1"
 
 
 class BatchNorm2Param(nn.Module):
@@ -301,6 +305,15 @@ class GraphResnetBlock(nn.Module):
         self.precision = 'fp32'
 
     def forward(self, x, edges, batch=None):
+        if _NVTX:                                   # STINET_NVTX=1: one range per block (nsys / ncu --nvtx timelines)
+            torch.cuda.nvtx.range_push(f"GraphResnetBlock {self.dim_in}->{self.dim_out} N={x.shape[0]}")
+            try:
+                return self._forward(x, edges, batch)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return self._forward(x, edges, batch)
+
+    def _forward(self, x, edges, batch=None):
         conv = self.first_filter(x, edges)
         if self.dim_in != self.dim_out:
             res = ops.linear(x, self.shortcut.weight, self.shortcut.bias, None, self.precision)
