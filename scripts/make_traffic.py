@@ -56,7 +56,9 @@ def main(tag):
                              "note": f"ncu --set full, {tag} ({part} capture): the longest launch of this kernel in one cfg2 step; "
                                      f"{rd / 1e6:.1f} MB read + {wr / 1e6:.1f} MB written in {us:.1f} us"}
     out = os.path.join(ROOT, "profiles", "traffic.json")
-    json.dump({"cfg2": best, "source": f"gpurun_out/prof_*_{tag}_raw.csv via scripts/make_traffic.py"}, open(out, "w"), indent=1)
+    for ent in best.values():
+        ent["source"] = f"gpurun_out/prof_*_{tag}_raw.csv via scripts/make_traffic.py"
+    json.dump({"cfg2": best}, open(out, "w"), indent=1)
     print(f"wrote {out}: {len(best)} families")
 
 
