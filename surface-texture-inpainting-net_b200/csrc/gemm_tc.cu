@@ -668,7 +668,11 @@ static int launch(const Problem& p, cudaStream_t s) {
   TcArgs g{p.C, p.ldc, p.bias, p.rowmask, (int)p.I, (int)p.J, (int)p.T, (int)p.t_per_split,
            tiles_j, tiles_i * tiles_j, (int)units,
            promote, C_::kFp32 ? (C_::kF16 ? 1 : env_split) : 0, p.a_exp, p.b_exp, p.splits == 1 ? p.amax_out : nullptr};
-  const unsigned grid = (unsigned)(units < kSMs ? units : kSMs);   // persistent: one CTA per SM walks the work units
+  // persistent: one CTA per SM walks the work units.  STINET_TC_SMS < 148 leaves SMs to kernels that run beside the GEMMs
+  // (NCCL's all-reduce CTAs during an overlapped backward: a persistent grid that cannot become fully resident at once
+  // pays a second wave for its last CTAs)
+  static const int env_sms = [] { const char* e = getenv("STINET_TC_SMS"); int v = e ? atoi(e) : kSMs; return v >= 1 && v <= kSMs ? v : kSMs; }();
+  const unsigned grid = (unsigned)(units < env_sms ? units : env_sms);
   K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, tmC, g));
   return check_launch("gemm_tc");
 }
