@@ -9,6 +9,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 
 from . import _abi
@@ -25,6 +27,24 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 def _require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise _abi.StinetError(f"{what} must live on a CUDA device (got {t.device}); stinet_b200 has no CPU path")
+
+
+_SIDE: Dict[tuple, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """The stream the structure of a batch is built on while the first layers already run (GraphCache.build_ahead)."""
+    k = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if k not in _SIDE:
+        _SIDE[k] = torch.cuda.Stream(device=dev)
+    return _SIDE[k]
+
+
+def _cuda_tensors(obj):
+    for v in vars(obj).values():
+        for t in (v if isinstance(v, (tuple, list)) else (v,)):
+            if torch.is_tensor(t) and t.is_cuda:
+                yield t
 
 
 def build_csr(key: torch.Tensor, other: Optional[torch.Tensor], n_rows: int, want_key32: bool = False,
@@ -62,6 +82,22 @@ class EdgeCSR:
         self._by_source = None
         self._tpos_s = None
 
+    _bwd_event = None     # set by GraphCache.build_ahead: the backward-only arrays were built on the side stream
+
+    def _wait_bwd(self) -> None:
+        ev = self._bwd_event
+        if ev is not None and torch.cuda.current_stream(self.rowptr_t.device) != _side_stream(self.rowptr_t.device):
+            torch.cuda.current_stream(self.rowptr_t.device).wait_event(ev)
+            self._bwd_event = None
+
+    def build_backward_parts(self, fused: bool) -> None:
+        """Everything only a backward pass reads: the by-source CSR and, for the fused EdgeConv node, the positions of
+        the saved ReLU masks and the dQ bound."""
+        self.by_source()
+        if fused:
+            self.tpos_s()
+            self.dq_factor()
+
     @classmethod
     def from_arrays(cls, n: int, rowptr_t, col_t, eid_t, rowptr_s, col_s, eid_s, tpos_s=None) -> "EdgeCSR":
         """Wrap arrays that already exist (stinet_b200.structure: built once per sample, concatenated per batch)."""
@@ -89,6 +125,7 @@ class EdgeCSR:
 
     def tpos_s(self) -> torch.Tensor:
         """By-target position of every by-source entry (where the saved ReLU masks of an out-edge live)."""
+        self._wait_bwd()
         if getattr(self, "_tpos_s", None) is None:
             _, _, eid_s = self.by_source()
             out = torch.empty(max(self.e, 1), dtype=torch.int32, device=self.rowptr_t.device)
@@ -100,6 +137,7 @@ class EdgeCSR:
 
     def by_source(self):
         """rowptr_s, col_s (= target vertex of each out-edge), eid_s -- only needed by backward passes."""
+        self._wait_bwd()
         if self._by_source is None:
             rowptr_s, eid_s, col_s, _ = build_csr(self._src, self._dst, self.n, status=self._status)
             self._by_source = (rowptr_s, col_s, eid_s)
@@ -121,6 +159,7 @@ class EdgeCSR:
     def dq_factor(self) -> torch.Tensor:
         """Device float: max_j sum_{j->i} 1/deg_i -- |dQ| <= max|dhid| * dq_factor in the message-stage backward (the
         bound its fp16 output planes are scaled with)."""
+        self._wait_bwd()
         if getattr(self, "_dq_factor", None) is None:
             rowptr_s, col_s, _ = self.by_source()
             out = torch.empty(1, dtype=torch.float32, device=self.rowptr_t.device)
@@ -225,6 +264,78 @@ class GraphCache:
         self._clusters: Dict[int, ClusterCSR] = {}
         self._segments: Dict[tuple, Segments] = {}
         self._gid: Dict[int, torch.Tensor] = {}
+        self._pending: Dict[tuple, "torch.cuda.Event"] = {}      # structures being built on the side stream
+        self._ahead = False
+        self._forked = False
+
+    # -- building the structure next to the first layers --------------------------------------------------------
+    def build_ahead(self, plan, backward: bool, fused: bool) -> None:
+        """plan: [("edges", key, level) | ("cluster", level) | ("gid", level)] in the order the forward first touches them.
+        The first entry is built on the current stream (the first layer needs it now); everything else, and the
+        backward-only arrays of every edge set, on a side stream that the current stream joins item by item when the item
+        is first asked for -- dozens of short launches that would otherwise sit in front of the first GEMM.  Works the
+        same eagerly and under CUDA-graph capture (the side stream forks from and rejoins the capturing stream).
+        STINET_STRUCT_SIDE_STREAM=0 keeps the lazy single-stream construction."""
+        if self._ahead:
+            return
+        self._ahead = True
+        if not plan or os.environ.get("STINET_STRUCT_SIDE_STREAM", "1") == "0":
+            return
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        first = plan[0]
+        built = []
+        if first[0] == "edges":
+            built.append(self.edges(first[1], first[2]))
+        side.wait_stream(main)
+        self._forked = True
+        objs = []
+        with torch.cuda.stream(side):
+            for item in plan[1:]:
+                k = tuple(item[:2])
+                if k in self._pending:
+                    continue
+                if item[0] == "edges":
+                    if item[1] in self._edges:
+                        continue
+                    o = self.edges(item[1], item[2])
+                    built.append(o)
+                elif item[0] == "cluster":
+                    if item[1] in self._clusters:
+                        continue
+                    o = self.cluster(item[1])
+                else:
+                    if item[1] in self._gid or self.batch_size <= 1:
+                        continue
+                    o = self.graph_id(item[1])
+                objs.append(o)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self._pending[k] = ev
+            if backward:
+                for e in built:
+                    if e._bwd_event is None and e._dst is not None:
+                        e.build_backward_parts(fused)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        e._bwd_event = ev
+        for o in objs + built:                          # allocated on the side stream, read on this one
+            for t in ([o] if torch.is_tensor(o) else _cuda_tensors(o)):
+                t.record_stream(main)
+
+    def join_ahead(self) -> None:
+        """The current stream waits for whatever build_ahead still has in flight (end of the forward)."""
+        if self._forked:
+            torch.cuda.current_stream(self.device).wait_stream(_side_stream(self.device))
+            self._forked = False
+            self._pending.clear()
+            for e in self._edges.values():
+                e._bwd_event = None
+
+    def _wait(self, k: tuple) -> None:
+        if k in self._pending and torch.cuda.current_stream(self.device) != _side_stream(self.device):
+            torch.cuda.current_stream(self.device).wait_event(self._pending.pop(k))
 
     @staticmethod
     def for_sample(sample, n_levels: int) -> "GraphCache":
@@ -239,6 +350,7 @@ class GraphCache:
 
     # -- structure ------------------------------------------------------------------------------------------
     def edges(self, key: str, level: int) -> EdgeCSR:
+        self._wait(("edges", key))
         if key not in self._edges:
             from .structure import prebuilt_edges
             pre = prebuilt_edges(self._sample, key, self.totals[level])     # cached per sample, batched by concatenation
@@ -250,6 +362,7 @@ class GraphCache:
 
     def cluster(self, level: int) -> ClusterCSR:
         """trace map level-1 -> level."""
+        self._wait(("cluster", level))
         if level not in self._clusters:
             from .structure import prebuilt_cluster
             pre = prebuilt_cluster(self._sample, level, self.totals[level - 1], self.totals[level])
@@ -265,6 +378,7 @@ class GraphCache:
         (reference :422 `batch = scatter_max(batch, trace)`)."""
         if self.batch_size <= 1:
             return None
+        self._wait(("gid", level))
         if level not in self._gid:
             if level == 0:
                 self._gid[0] = self._sample.batch.to(torch.int32).contiguous()

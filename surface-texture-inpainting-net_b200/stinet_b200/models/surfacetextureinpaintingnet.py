@@ -209,6 +209,21 @@ class SurfaceTextureInpaintingNet(nn.Module):
             wp = self._wplanes = ops.WeightPlanes(entries)
         wp.refresh()
 
+    def _structure_plan(self, L, batch_size):
+        """The structure of a batch in the order forward() first touches it (GraphCache.build_ahead)."""
+        plan = [("edges", 'edge_index', 0)]
+        if batch_size > 1:
+            plan.append(("gid", 0))
+        for level in range(1, L + 1):
+            plan.append(("cluster", level))
+            if batch_size > 1:
+                plan.append(("gid", level))
+            plan.append(("edges", f"hierarchy_edge_index_{level}", level))
+        for d in self.dilations[:len(self.bottleneck_blocks)]:
+            if d > 1:
+                plan.append(("edges", f"hierarchy_dil_{d}_edge_index_{L}", L))
+        return plan
+
     def _pooling(self, vertex_features, cluster):
         if self._pooling_type == 'mean':
             return ops.pool_mean(vertex_features, cluster)
@@ -232,6 +247,9 @@ class SurfaceTextureInpaintingNet(nn.Module):
         if sample.x.is_cuda and self.precision in ('fp32', 'f16'):
             self._refresh_weight_planes()
 
+        if sample.x.is_cuda:
+            cache.build_ahead(self._structure_plan(L, cache.batch_size), torch.is_grad_enabled(),
+                              self.precision in ('fp32', 'f16'))
         out = sample.x
         e0 = cache.edges('edge_index', 0)
         for block in self.input_blocks:
@@ -275,6 +293,7 @@ class SurfaceTextureInpaintingNet(nn.Module):
             out = ops.norm_act_res(out, None, None, False, ACT_ELU)
         else:
             out = nn.functional.elu(self.final_norm1(out, final_seg))
+        cache.join_ahead()
         fused = ops.head_tanh(out, self.final_linear2.weight, self.final_linear2.bias)   # Linear(ngf, 3) + Tanh in one kernel
         if fused is not None:
             return fused

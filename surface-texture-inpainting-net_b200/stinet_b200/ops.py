@@ -45,6 +45,96 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------------------
+# weight gradients next to the data-gradient chain
+#
+# In a backward pass only the data gradients are on the critical path (dgrad -> message-stage backward -> dgrad ...);
+# the weight gradients (wgrad GEMM, its split reduction, the un-hoisting of dWcat) are leaves that nothing reads before
+# the optimizer.  They are launched on a second stream, so the tail of a dgrad kernel that no longer fills the 148 SMs
+# overlaps with the head of the wgrad next to it (and the other way round); in a captured step these are parallel branches
+# of the CUDA graph.  STINET_WGRAD_SIDE_STREAM = 0: one stream; 1: the node's backward joins before it returns;
+# 2 (default): joined once, at the end of the backward pass (autograd's final callback) and before a gradient bucket is
+# packed (parallel.GradAllReducer) -- buffers the second stream reads are then kept from reuse by record_stream.
+_WGRAD_SIDE = int(os.environ.get("STINET_WGRAD_SIDE_STREAM", "2"))
+_WGRAD_STREAMS = {}
+_wgrad_join_due = set()
+
+
+def _wgrad_stream(dev: torch.device):
+    k = dev.index if dev.index is not None else torch.cuda.current_device()
+    if k not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[k] = torch.cuda.Stream(device=dev)
+    return _WGRAD_STREAMS[k]
+
+
+class _on_wgrad_stream:
+    """with _on_wgrad_stream(dev, reads): ...   launches of the body go to the weight-gradient stream, after everything
+    issued so far on the current one.  `reads`: Planes / tensors of the current stream the body reads."""
+
+    def __init__(self, dev, reads=()):
+        self.dev, self.reads, self.ctx = dev, reads, None
+
+    def __enter__(self):
+        if not _WGRAD_SIDE:
+            return self
+        main, side = torch.cuda.current_stream(self.dev), _wgrad_stream(self.dev)
+        side.wait_stream(main)
+        if _WGRAD_SIDE == 2:
+            for r in self.reads:
+                for t in ((r.hi, r.lo, r.exp) if isinstance(r, Planes) else (r,)):
+                    if t is not None:
+                        t.record_stream(side)
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_wgrad_stream(dev=None) -> None:
+    """The current stream waits for the weight gradients launched so far (no-op when nothing is in flight)."""
+    for k in ([dev.index if dev.index is not None else torch.cuda.current_device()] if dev is not None
+              else list(_wgrad_join_due)):
+        if k in _wgrad_join_due:
+            _wgrad_join_due.discard(k)
+            torch.cuda.current_stream(k).wait_stream(_WGRAD_STREAMS[k])
+
+
+def _straight_to_grad(*weights) -> bool:
+    """True when the gradients of these weights go from the backward straight into `.grad` by reference (leaf parameter,
+    no gradient yet, no tensor hooks, post-accumulate hooks only from GradAllReducer, which joins before it packs):
+    nothing on the current stream reads them before the end of the backward pass, so their join can wait until then.
+    A weight that is itself a function of a parameter (a padded or hoisted copy) has an autograd node downstream that
+    reads the gradient at once -- its backward joins before it returns."""
+    for w in weights:
+        if w is None:
+            continue
+        if not w.is_leaf or w.grad is not None or w._backward_hooks:
+            return False
+        if getattr(w, "_post_accumulate_grad_hooks", None) and not getattr(w, "_stinet_wgrad_aware", False):
+            return False
+    return True
+
+
+def _wgrad_done(dev, outs, defer_ok: bool = True) -> None:
+    """End of a backward that used _on_wgrad_stream: `outs` were produced there and are consumed on the current stream."""
+    if not _WGRAD_SIDE:
+        return
+    main = torch.cuda.current_stream(dev)
+    for t in outs:
+        if t is not None:
+            t.record_stream(main)
+    k = dev.index if dev.index is not None else torch.cuda.current_device()
+    _wgrad_join_due.add(k)
+    if _WGRAD_SIDE == 1 or not defer_ok:
+        join_wgrad_stream(dev)
+    else:                                            # idempotent: the first one to run joins, the others find nothing due
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: join_wgrad_stream(dev))
+
+
+# ------------------------------------------------------------------------------------------------------------
 # dense layers
 
 
@@ -328,6 +418,7 @@ class LinearPlanesFn(Function):
         y, LinearPlanesFn.last_amax = _pl_fwd(xp, wp, bias, rowmask, passes, want_amax=True)
         ctx.xp, ctx.wp, ctx.rowmask = xp, wp, rowmask
         ctx.has_bias, ctx.passes = bias is not None, passes
+        ctx.weights = (weight,)
         return y
 
     @staticmethod
@@ -339,10 +430,14 @@ class LinearPlanesFn(Function):
             dyp, db = planes_and_colsum(dy, rowmask, passes == 3)
         else:
             dyp = planes_of(dy, passes == 3)
+        dev = dy.device
+        if ctx.needs_input_grad[1]:
+            with _on_wgrad_stream(dev, (dyp, xp)):
+                dw = _pl_wgrad(dyp, xp, passes)
         if ctx.needs_input_grad[0]:
             dx, _ = _pl_dgrad(dyp, wp, passes)
-        if ctx.needs_input_grad[1]:
-            dw = _pl_wgrad(dyp, xp, passes)
+        if dw is not None:
+            _wgrad_done(dev, (dw,), _straight_to_grad(*ctx.weights))
         return dx, dw, db, None, None
 
 
@@ -397,6 +492,7 @@ class EdgeConvFn(Function):
         if train:
             ctx.saved = (xp, wcp, hidp, w2p, mask, csr)
         ctx.dims = (n, din, h, kin, dout, trans_inv, passes, b0 is not None, b2 is not None)
+        ctx.weights = (w0, w2)
         return y
 
     @staticmethod
@@ -414,8 +510,11 @@ class EdgeConvFn(Function):
         else:
             dyp = planes_of(dy, need_lo)
         # second Linear
+        dw2 = None
+        if ctx.needs_input_grad[3]:
+            with _on_wgrad_stream(dev, (dyp, hidp)):
+                dw2 = _pl_wgrad(dyp, hidp, passes)
         dhid, dhid_amax = _pl_dgrad(dyp, w2p, passes, want_amax=True)
-        dw2 = _pl_wgrad(dyp, hidp, passes) if ctx.needs_input_grad[3] else None
         # message stage: dPQ = [dP | dQ] as planes
         rowptr_s, col_s, _ = csr.by_source()
         dpqp = _new_planes(n, 2 * h, need_lo, dev)
@@ -428,13 +527,16 @@ class EdgeConvFn(Function):
                   n, h, dpqp.hi.data_ptr(), _ptr(dpqp.lo), dpqp.ld, dpqp.exp.data_ptr(), _ptr(db0), _ptr(wse), nbe, s,
                   cost=(csr.e * (4 * h + h // 2 + 12) + n * (16 * h + 8), 2 * csr.e * h, f"H{h}"))
         # first (hoisted) Linear
-        dx = _pl_dgrad(dpqp, wcp, passes)[0] if ctx.needs_input_grad[0] else None
         dw0 = None
         if ctx.needs_input_grad[1]:
-            dwcat = _pl_wgrad(dpqp, xp, passes)
-            dw0 = torch.empty((h, kin), dtype=torch.float32, device=dev)
-            _abi.call("stinet_edgeconv_hoist_bwd", dwcat.data_ptr(), None, h, din, int(trans_inv), dw0.data_ptr(), kin, None,
-                      s, cost=(4 * h * (kin + 2 * din), 0, ""))
+            with _on_wgrad_stream(dev, (dpqp, xp)):
+                dwcat = _pl_wgrad(dpqp, xp, passes)
+                dw0 = torch.empty((h, kin), dtype=torch.float32, device=dev)
+                _abi.call("stinet_edgeconv_hoist_bwd", dwcat.data_ptr(), None, h, din, int(trans_inv), dw0.data_ptr(), kin,
+                          None, _stream(), cost=(4 * h * (kin + 2 * din), 0, ""))
+        dx = _pl_dgrad(dpqp, wcp, passes)[0] if ctx.needs_input_grad[0] else None
+        if dw0 is not None or dw2 is not None:
+            _wgrad_done(dev, (dw0, dw2), _straight_to_grad(*ctx.weights))
         return dx, dw0, db0, dw2, db2, None, None, None
 
 

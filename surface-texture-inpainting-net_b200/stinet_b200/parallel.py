@@ -88,6 +88,7 @@ class GradAllReducer:
         self._issued = [False] * len(self._groups)
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._on_grad)
+            p._stinet_wgrad_aware = True             # ops._straight_to_grad: _issue() joins the weight-gradient stream
 
     def zero_grad(self):
         """Gradients are handed over by autograd as fresh tensors (no zero-fill, no accumulate pass)."""
@@ -101,6 +102,8 @@ class GradAllReducer:
     def _issue(self, b: int):
         """Pack bucket b (one multi-tensor copy; a parameter without a gradient contributes zeros), re-point the .grad of
         its parameters at the flat buffer and start the all-reduce."""
+        from . import ops
+        ops.join_wgrad_stream()                      # weight gradients still in flight on their own stream
         group, views = self._groups[b], self._views[b]
         have = [(v, p.grad) for v, p in zip(views, group) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         for v, p in zip(views, group):

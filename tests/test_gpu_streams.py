@@ -1,0 +1,87 @@
+"""The two concurrency devices of a step -- the batch's structure built on a side stream next to the first layers
+(GraphCache.build_ahead) and the weight gradients on a second stream next to the data-gradient chain
+(ops._on_wgrad_stream) -- must not change a single bit: same loss and same gradients as the one-stream schedule,
+eagerly and when the step is replayed from a CUDA graph several times."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _loss(out, b):
+    composed = torch.where((b.mask > 0).expand_as(b.color), out, b.color)
+    return ((composed - b.color).abs() * torch.pow(0.99, b.mask.squeeze().float()).unsqueeze(1)).mean()
+
+
+def _make(seed):
+    from stinet_b200 import synthetic
+    return synthetic.make_batch("icosphere", 3, 2, seed=seed, subdiv=4, mask_radius=3)
+
+
+def _net():
+    from stinet_b200.models import surfacetextureinpaintingnet as S
+    torch.manual_seed(49)
+    return S.define_G(input_nc=10, output_nc=3, ngf=32, filter_type="edgeconv", norm="instance", n_blocks=3,
+                      n_levels=2, pooling_type="max", gpu_ids=[torch.device(DEV)]).train()
+
+
+def _grads(monkeypatch, struct_side: str, wgrad_side: int, reps: int = 3):
+    from stinet_b200 import ops
+    monkeypatch.setenv("STINET_STRUCT_SIDE_STREAM", struct_side)
+    monkeypatch.setattr(ops, "_WGRAD_SIDE", wgrad_side)
+    net = _net()
+    out = []
+    for r in range(reps):
+        b = _make(49 + r).to(DEV)
+        net.zero_grad(set_to_none=True)
+        loss = _loss(net(b), b)
+        loss.backward()
+        torch.cuda.synchronize()
+        out.append((float(loss.item()), [p.grad.detach().clone() for p in net.parameters()]))
+    return out
+
+
+@pytest.mark.parametrize("struct_side,wgrad_side", [("1", 0), ("0", 1), ("0", 2), ("1", 2)])
+def test_side_streams_do_not_change_a_bit(monkeypatch, struct_side, wgrad_side):
+    ref = _grads(monkeypatch, "0", 0)
+    got = _grads(monkeypatch, struct_side, wgrad_side)
+    for (l0, g0), (l1, g1) in zip(ref, got):
+        assert l0 == l1
+        for a, b in zip(g0, g1):
+            assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("wgrad_side", [1, 2])
+def test_side_streams_inside_a_captured_step(monkeypatch, wgrad_side):
+    from stinet_b200 import ops
+    from stinet_b200.engine import GraphedTrainStep
+    batches = [_make(49), _make(50), _make(51), _make(49)]
+
+    def run(struct_side, wg, graphed):
+        monkeypatch.setenv("STINET_STRUCT_SIDE_STREAM", struct_side)
+        monkeypatch.setattr(ops, "_WGRAD_SIDE", wg)
+        net = _net()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, amsgrad=True, fused=True, capturable=True)
+        losses = []
+        if graphed:
+            step = GraphedTrainStep(net, _loss, opt, warmup=1)
+            for b in batches:
+                losses.append(float(step(b.pin_memory()).item()))
+            assert step.captures == 1
+        else:
+            for b in batches:
+                gb = b.to(DEV)
+                opt.zero_grad(set_to_none=True)
+                loss = _loss(net(gb), gb)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.item()))
+        torch.cuda.synchronize()
+        return losses, [p.detach().clone() for p in net.parameters()]
+
+    l0, p0 = run("0", 0, False)
+    l1, p1 = run("1", wgrad_side, True)
+    assert l0 == l1, (l0, l1)
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)
