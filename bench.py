@@ -474,12 +474,25 @@ def main():
         for _ in range(2):                                   # the eager steps all-reduce: every rank has to take part
             eager_step(resident)
     if rank == 0 and not args.no_profile:
-        with _abi.KernelProfiler() as prof:                  # per-kernel CUDA events need eager launches
-            for _ in range(2):
-                # let the host run ahead of the device: ~60 ms of idle spinning on the stream while Python enqueues the
-                # step's ~650 launches, so that the event pairs bracket device time, not the host's launch gaps
-                torch.cuda._sleep(120_000_000)
-                eager_step(resident)
+        # a kernel's duration is taken with the kernel alone on the GPU: the profiled eager steps use the one-stream
+        # schedule (the timed step overlaps the structure build and the weight gradients with the main chain, which
+        # stretches every event pair that brackets two kernels sharing the SMs)
+        from stinet_b200 import ops as _ops
+        side_env, side_wgrad = os.environ.get("STINET_STRUCT_SIDE_STREAM"), _ops._WGRAD_SIDE
+        os.environ["STINET_STRUCT_SIDE_STREAM"], _ops._WGRAD_SIDE = "0", 0
+        try:
+            with _abi.KernelProfiler() as prof:              # per-kernel CUDA events need eager launches
+                for _ in range(2):
+                    # let the host run ahead of the device: ~60 ms of idle spinning on the stream while Python enqueues
+                    # the step's ~650 launches, so that the event pairs bracket device time, not the host's launch gaps
+                    torch.cuda._sleep(120_000_000)
+                    eager_step(resident)
+        finally:
+            _ops._WGRAD_SIDE = side_wgrad
+            if side_env is None:
+                os.environ.pop("STINET_STRUCT_SIDE_STREAM", None)
+            else:
+                os.environ["STINET_STRUCT_SIDE_STREAM"] = side_env
         summ = prof.summary()
         total = sum(r["ms"] for r in summ.values())
         kernels = {k: {"calls_per_step": r["calls"] // 2, "ms_per_step": round(r["ms"] / 2, 4),
@@ -526,6 +539,8 @@ def main():
                 roofline["path"]["roofline_ms_per_step_mode_ceiling"] / (ms / K)
         except Exception as e:  # noqa: BLE001
             roofline["path"] = {"error": repr(e)}
+        roofline["schedule"] = ("per-kernel durations: eager launches on one stream (each kernel alone on the GPU); the timed "
+                                "step overlaps structure build and weight gradients with the main chain on side streams")
         roofline["share_of_step"] = r["ms"] / total
         roofline["ms_per_launch"] = r["ms"] / r["calls"]
         # measured DRAM traffic per launch of the dominant kernels (ncu --set full, profiles/): largest shape of each

@@ -198,11 +198,14 @@ int stinet_segnorm_apply(const float* x, int64_t ldx, int64_t n_rows, int64_t ch
 /* backward of out = act(norm(x)):  dx = rstd*(dz - mean_s(dz) - yhat*mean_s(dz*yhat)), dz = dout*act'(yhat).
  * Requires slices == true segments (gid constant on every slice); otherwise STINET_ERR_UNSUPPORTED is the
  * caller's job to raise (the library cannot see it without a sync).  gid == NULL: a row uses the statistics of the
- * slice that contains it (single cluster kernel for slices of at most 16384 rows, as in stinet_segnorm_fwd). */
+ * slice that contains it (single cluster kernel for slices of at most 16384 rows, as in stinet_segnorm_fwd).
+ * dout_amax (nullable, float[1]): max|dout|, taken by the pass that reads dout anyway -- dout is also the gradient of the
+ * block's shortcut branch (x' = shortcut(x) + ..., :521), whose dense layer then needs no reduction pass of its own. */
 int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows, int64_t channels,
                        int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr, const float* cnt,
                        const int32_t* gid, const float* mean, const float* rstd, int act, float* dx, int64_t lddx,
-                       float* amax_out, void* workspace, size_t workspace_bytes, stinet_stream_t stream);
+                       float* amax_out, float* dout_amax, void* workspace, size_t workspace_bytes,
+                       stinet_stream_t stream);
 
 /* ---- affine segmented norms: the alternative norm_type modules of the network and the BatchNorm1d
  * over the EDGES inside SingleConvMeshNet's message MLP, all of the form

@@ -47,6 +47,7 @@ struct NormArgs {
   const float* mean; const float* rstd;
   float* part0; float* part1;
   int channels; int max_chunks; int act;
+  unsigned* aux_amax;                  // MODE_BWD, nullable: max |dout| as a bit pattern (atomicMax into a zeroed slot)
 };
 
 template <int MODE, bool VEC>
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(kNormThreads) seg_colreduce_kernel(NormArgs a)
   const int r0 = a.slice_ptr[s] + blockIdx.x * kChunkRows;
   const int r1 = min(r0 + kChunkRows, a.slice_ptr[s + 1]);
   float acc0[W], acc1[W];
+  unsigned dmax = 0u;
 #pragma unroll
   for (int w = 0; w < W; ++w) acc0[w] = acc1[w] = 0.f;
   if (grp < groups && ty < tyn) {
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(kNormThreads) seg_colreduce_kernel(NormArgs a)
             } else {
               const float yh = (v[u][w] - m) * rs;
               const float dz = (a.act == STINET_ACT_ELU) ? d[u][w] * elu1_grad(yh) : d[u][w];
+              dmax = max(dmax, __float_as_uint(d[u][w]) & 0x7FFFFFFFu);
               acc0[w] += dz;
               acc1[w] += dz * yh;
             }
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(kNormThreads) seg_colreduce_kernel(NormArgs a)
       if (MODE == MODE_BWD) a.part1[o + w] = t1;
     }
   }
+  if (MODE == MODE_BWD && a.aux_amax != nullptr) amax_publish(dmax, a.aux_amax);
 }
 
 // FIN: 0 -> out = sum/cnt ; 1 -> out = 1/sqrt(sum/cnt + eps).  One CTA per (32 channels, segment): 32 channel lanes x
@@ -344,6 +348,7 @@ struct FusedArgs {
   int channels; int act; float eps;
   unsigned* amax_out;                  // nullable: max |out| as a bit pattern (atomicMax into a zeroed slot)
   PlaneOut po;                         // fwd: optional fp16 planes of out
+  unsigned* aux_amax;                  // bwd, nullable: max |dout| as a bit pattern
 };
 
 __device__ __forceinline__ float4 f4add(const float4& a, const float4& b) {
@@ -498,6 +503,7 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedAr
   const float4 rs = col ? reinterpret_cast<const float4*>(a.rstd + (int64_t)s * a.channels)[c4] : zero;
   const bool elu = a.act == STINET_ACT_ELU;
   // (yhat, dz) of one element quad
+  unsigned dmax = 0u;
   auto prep = [&](const float4& xv, const float4& dv, float4& yh, float4& dz) {
     yh = make_float4((xv.x - m.x) * rs.x, (xv.y - m.y) * rs.y, (xv.z - m.z) * rs.z, (xv.w - m.w) * rs.w);
     dz = dv;
@@ -518,6 +524,7 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedAr
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
       prep(xv[i], dv[i], yhc[i], dzc[i]);     // padded rows: yhat = 0, dz = 0 -> contribute exactly 0
+      dmax = amax4(dmax, dv[i]);
       acc0 = f4add(acc0, dzc[i]);
       acc1.x += dzc[i].x * yhc[i].x; acc1.y += dzc[i].y * yhc[i].y; acc1.z += dzc[i].z * yhc[i].z; acc1.w += dzc[i].w * yhc[i].w;
     }
@@ -534,6 +541,7 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedAr
       for (int u = 0; u < 4; ++u) {
         float4 yh, dz;
         prep(xv[u], dv[u], yh, dz);
+        dmax = amax4(dmax, dv[u]);
         acc0 = f4add(acc0, dz);
         acc1.x += dz.x * yh.x; acc1.y += dz.y * yh.y; acc1.z += dz.z * yh.z; acc1.w += dz.w * yh.w;
       }
@@ -577,6 +585,7 @@ __global__ void __launch_bounds__(kNormThreads) segnorm_fused_bwd_kernel(FusedAr
     }
   }
   if (a.amax_out != nullptr) amax_publish(amax_bits, a.amax_out);
+  if (a.aux_amax != nullptr) amax_publish(dmax, a.aux_amax);
   cluster.sync();
 }
 
@@ -886,14 +895,16 @@ extern "C" int stinet_segnorm_fwd(const float* x, int64_t ldx, int64_t n_rows, i
 extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout, int64_t ldg, int64_t n_rows,
                                   int64_t channels, int64_t n_seg, int64_t max_seg_rows, const int32_t* slice_ptr,
                                   const float* cnt, const int32_t* gid, const float* mean, const float* rstd, int act,
-                                  float* dx, int64_t lddx, float* amax_out, void* workspace, size_t workspace_bytes,
-                                  stinet_stream_t stream_) {
+                                  float* dx, int64_t lddx, float* amax_out, float* dout_amax, void* workspace,
+                                  size_t workspace_bytes, stinet_stream_t stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   unsigned* am = reinterpret_cast<unsigned*>(amax_out);
-  if (am != nullptr) {
-    cudaError_t e = cudaMemsetAsync(am, 0, sizeof(unsigned), s);
-    STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "segnorm_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
-  }
+  unsigned* dam = reinterpret_cast<unsigned*>(dout_amax);
+  for (unsigned* slot : {am, dam})
+    if (slot != nullptr) {
+      cudaError_t e = cudaMemsetAsync(slot, 0, sizeof(unsigned), s);
+      STINET_REQUIRE(e == cudaSuccess, STINET_ERR_CUDA, "segnorm_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
   STINET_REQUIRE(x && dout && dx && ((mean == nullptr) == (rstd == nullptr)), STINET_ERR_ARG, "segnorm_bwd: null pointer");
   STINET_REQUIRE(n_rows >= 0 && channels > 0 && ldx >= channels && ldg >= channels && lddx >= channels,
                  STINET_ERR_ARG, "segnorm_bwd: bad shape");
@@ -907,7 +918,7 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     STINET_REQUIRE(slice_ptr && cnt && n_seg > 0 && n_seg <= 65535, STINET_ERR_ARG, "segnorm_bwd: segments required");
     const FusedPlan pl = fused_plan(max_seg_rows);
     FusedArgs a{x, ldx, dout, ldg, slice_ptr, cnt, const_cast<float*>(mean), const_cast<float*>(rstd), dx, lddx,
-                (int)channels, act, 0.f, am, PlaneOut{nullptr, nullptr, 0, nullptr, 0.f, nullptr}};
+                (int)channels, act, 0.f, am, PlaneOut{nullptr, nullptr, 0, nullptr, 0.f, nullptr}, dam};
     return pl.cached ? launch_fused(segnorm_fused_bwd_kernel<kFusedRR>, a, n_seg, pl.cluster, s)
                      : launch_fused(segnorm_fused_bwd_kernel<0>, a, n_seg, pl.cluster, s);
   }
@@ -916,8 +927,9 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
     NormWs w = carve_norm(workspace, max_seg_rows, channels, n_seg);
     STINET_REQUIRE(workspace && workspace_bytes >= w.bytes, STINET_ERR_WORKSPACE, "segnorm_bwd: workspace %zu < %zu",
                    workspace_bytes, w.bytes);
-    NormArgs a{x, ldx, dout, ldg, slice_ptr, gid, mean, rstd, w.part0, w.part1, (int)channels, w.max_chunks, act};
+    NormArgs a{x, ldx, dout, ldg, slice_ptr, gid, mean, rstd, w.part0, w.part1, (int)channels, w.max_chunks, act, dam};
     launch_colreduce<MODE_BWD>(vec, a, n_seg, s);
+    dam = nullptr;                                      // done by the reduction pass
     const dim3 fin_grid((unsigned)ceil_div(channels, 32), (unsigned)n_seg);
     K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.part0, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s1));
     K(seg_finalize_kernel<0><<<fin_grid, 1024, 0, s>>>(w.part1, slice_ptr, cnt, (int)n_seg, (int)channels, w.max_chunks, 0.f, w.s2));
@@ -938,6 +950,7 @@ extern "C" int stinet_segnorm_bwd(const float* x, int64_t ldx, const float* dout
   else K(segnorm_bwd_apply_kernel<false><<<grid, kNormThreads, 0, s>>>(x, ldx, dout, ldg, n_rows, (int)channels, gid, mean, rstd, s1, s2, act, dx, lddx));
   int rc = check_launch("segnorm_bwd");
   if (rc == STINET_OK && amax_out != nullptr) rc = stinet_f16_amax(dx, lddx, n_rows, channels, amax_out, stream_);
+  if (rc == STINET_OK && dam != nullptr) rc = stinet_f16_amax(dout, ldg, n_rows, channels, dout_amax, stream_);  // no reduction pass ran
   return rc;
 }
 

@@ -46,7 +46,7 @@ SIGNATURES = {
     "stinet_segnorm_stats": (I, [P, I64, I64, I64, I64, I64, P, P, P, F, P, P, P, SZ, P]),
     "stinet_segnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, F, P, I64, I, P, I64, P, P, P, P, P, I64, P, P, P, SZ, P]),
     "stinet_segnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, I64, I, P, I64, P]),
-    "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, P, SZ, P]),
+    "stinet_segnorm_bwd": (I, [P, I64, P, I64, I64, I64, I64, I64, P, P, P, P, P, I, P, I64, P, P, P, SZ, P]),
     "stinet_affnorm_workspace_bytes": (SZ, [I64, I64, I64]),
     "stinet_affnorm_fwd": (I, [P, I64, I64, I64, I64, I64, P, P, P, I, F, P, P, P, P, I64, P, P, P, SZ, P]),
     "stinet_affnorm_apply": (I, [P, I64, I64, I64, P, P, P, P, P, P, P, I64, P]),

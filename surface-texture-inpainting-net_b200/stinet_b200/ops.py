@@ -936,6 +936,7 @@ class NormActResFn(Function):
     def backward(ctx, dout):
         x, mean, rstd = ctx.saved_tensors
         seg = ctx.seg
+        dout_in = dout
         dout = _mat(dout)
         n, c = x.shape
         dx = None
@@ -948,17 +949,22 @@ class NormActResFn(Function):
                     return dx, dres, None, None, None, None
                 nb = _abi.query("stinet_segnorm_workspace_bytes", seg.max_seg_rows, c, seg.n_seg)
                 ws = _ws(nb, x.device)
-                amax = torch.empty(1, dtype=torch.float32, device=x.device)
+                amax = torch.empty(2, dtype=torch.float32, device=x.device)
+                # dout is also the gradient of the shortcut branch: its Linear's backward reads max|dout| from here
+                want_dmax = ctx.has_res and ctx.needs_input_grad[1] and getattr(dout, "_stinet_amax", None) is None
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, seg.n_seg,
                           seg.max_seg_rows, seg.slice_ptr.data_ptr(), seg.cnt.data_ptr(),
                           None if (seg.n_seg == 1 or _vec_ok(c, x, dout)) else _ptr(seg.gid),
-                          mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, amax.data_ptr(), ws.data_ptr(), nb,
+                          mean.data_ptr(), rstd.data_ptr(), ctx.act, dx.data_ptr(), c, amax.data_ptr(),
+                          amax.data_ptr() + 4 if want_dmax else None, ws.data_ptr(), nb,
                           _stream(), cost=(16 * n * c, 10 * n * c, f"C{c}"))
-                set_amax(dx, amax)                       # the conv's backward splits dx into planes next
+                set_amax(dx, amax[0:1])                  # the conv's backward splits dx into planes next
+                if want_dmax:
+                    set_amax(dout_in, amax[1:2])
             else:
                 _abi.call("stinet_segnorm_bwd", x.data_ptr(), _ld(x), dout.data_ptr(), _ld(dout), n, c, 1, n, None,
-                          None, None, None, None, ctx.act, dx.data_ptr(), c, None, None, 0, _stream())
-        dres = dout if (ctx.has_res and ctx.needs_input_grad[1]) else None
+                          None, None, None, None, ctx.act, dx.data_ptr(), c, None, None, None, 0, _stream())
+        dres = dout_in if (ctx.has_res and ctx.needs_input_grad[1]) else None
         return dx, dres, None, None, None, None
 
 
