@@ -5,13 +5,13 @@
 // Each operand is either "K-major" (t contiguous in HBM:  A'(i,t) = A[i*ld + t]) or "MN-major" (i / j contiguous:
 // A'(i,t) = A[t*ld + i]); that covers  fwd (K,K),  dgrad (K,MN)  and  wgrad (MN,MN, split over t with a fixed-order
 // second-stage reduction done by the caller).  Persistent kernel: one CTA per SM walks the 128 x BN output tiles
-// (x reduction splits), 14 warps with fixed roles:
+// (x reduction splits), 10 warps with fixed roles (14 in the one mode that splits its operands in shared memory):
 //
 //   warp 0    : TMA producer  -- cp.async.bulk.tensor loads 128B-swizzled operand tiles into a kStages-deep smem ring
 //   warp 1    : MMA issuer    -- one elected thread issues tcgen05.mma (M=128, N=BN) into one of TWO TMEM accumulator
 //                                buffers; tcgen05.commit releases smem stages and hands finished buffers to the epilogue
-//   warps 2-5 : (fp32 mode) in-smem operand split  x = hi + lo  between the TMA and the MMA
-//   warps 6-13: epilogue      -- tcgen05.ld TMEM -> registers; in fp32 mode the partial sums of every 128 reduction
+//   warps 2-5 : (TF32X3 only) in-smem operand split  x = hi + lo  between the TMA and the MMA
+//   last 8    : epilogue      -- tcgen05.ld TMEM -> registers; in fp32 mode the partial sums of every 128 reduction
 //                                elements are added round-to-nearest into register accumulators (the tensor core's own
 //                                fp32 accumulation truncates); then (+bias) -> swizzled smem transpose -> coalesced
 //                                128-bit stores.  The epilogue of tile n overlaps the main loop of tile n+1.
@@ -38,9 +38,7 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int kConvWarps = 4;                            // operand-split warps (fp32 mode)
-constexpr int kEpiWarps = 8;                             // epilogue warps: TMEM lane quarter = warp % 4, column half = (warp-6)/4
-constexpr int kEpiWarp0 = 2 + kConvWarps;
-constexpr int kThreads = 32 * (2 + kConvWarps + kEpiWarps);  // 448
+constexpr int kEpiWarps = 8;                             // epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - first) / 4
 constexpr uint32_t kRowBytes = 128;  // one swizzle row: 32 fp32 or 64 bf16 along the contiguous dimension
 constexpr uint32_t kStagingBytes = kEpiWarps * 32 * 32 * 4;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
 
@@ -214,6 +212,11 @@ struct Cfg {
   static constexpr bool kPre = MODE == MODE_BF16X3 || MODE == MODE_TF32X3P || MODE == MODE_F16X3;  // split done by the caller in HBM
   static constexpr bool kFp32 = MODE == MODE_TF32X3 || MODE == MODE_TF32X3P || MODE == MODE_F16X3; // fp32-class result: promotion + correction accumulator
   static constexpr bool kSplit = kConv || kPre;                    // stage holds hi and lo tiles, three MMAs per k-step
+  // warps: 0 TMA producer, 1 MMA issuer, [2, kEpiWarp0) operand split (only the mode that splits in shared memory has
+  // them: registers are handed out per 4 warps, 10 warps leave 170 per thread where 14 leave 128 -- the epilogue's
+  // 64 + 32 + 32 live accumulator values then fit without spills), then 8 epilogue warps
+  static constexpr int kEpiWarp0 = 2 + (kConv ? kConvWarps : 0);
+  static constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
   // F16X3: the B planes sit back to back in the stage ([A_hi][A_lo][B_hi][B_lo]) and the main / correction accumulators
   // back to back in TMEM, so ONE MMA of width 2*BN evaluates A_hi * [B_hi ; B_lo]^T = [hi*hi | hi*lo] and a second one
   // adds A_lo * B_hi^T to the correction half: A_hi is read from shared memory once instead of twice per k-step
@@ -240,7 +243,7 @@ struct Cfg {
 };
 
 template <int BN, bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<BN, MODE>::kThreads), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmC, TcArgs g) {
@@ -421,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       DBG_FLUSH(true, 6, 6);
       DBG_FLUSH(true, 8, 8);
     }
-  } else if (warp < kEpiWarp0) {
+  } else if (warp < C_::kEpiWarp0) {
     // ===== operand split (fp32 mode): x = hi + lo, hi = x rounded to TF32 (written in place), lo = x - hi (exact in
     // fp32; the tensor core keeps its top 11 significand bits).  Element-wise, so the swizzled layouts are untouched.
     if (C_::kConv) {
@@ -472,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue: TMEM -> registers (RN accumulation across promotion chunks) -> swizzled smem transpose ->
     // coalesced 128-bit global stores =====
-    const int ew = warp - kEpiWarp0;
+    const int ew = warp - C_::kEpiWarp0;
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int h = ew >> 2;             // column half
     constexpr int EC = C_::kEpiCols;
@@ -557,7 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0 && amax_bits > *reinterpret_cast<volatile unsigned*>(g.amax_out)) atomicMax(g.amax_out, amax_bits);
     }
     if (lane == 0) bulk_wait_all();
-    DBG_FLUSH(threadIdx.x == 32 * kEpiWarp0, 4, 5);
+    DBG_FLUSH(threadIdx.x == 32 * C_::kEpiWarp0, 4, 5);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -673,7 +676,7 @@ static int launch(const Problem& p, cudaStream_t s) {
   // pays a second wave for its last CTAs)
   static const int env_sms = [] { const char* e = getenv("STINET_TC_SMS"); int v = e ? atoi(e) : kSMs; return v >= 1 && v <= kSMs ? v : kSMs; }();
   const unsigned grid = (unsigned)(units < env_sms ? units : env_sms);
-  K(kern<<<grid, kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, tmC, g));
+  K(kern<<<grid, C_::kThreads, C_::kSmemBytes, s>>>(tmA, tmB, tmA2, tmB2, tmC, g));
   return check_launch("gemm_tc");
 }
 
