@@ -23,21 +23,20 @@ from ._structure import as_edge_csr
 
 
 class EdgeConv(torch.nn.Module):
-    """x_i' = mean_{j->i} nn([x_i || x_j - x_i])   (PyG EdgeConv with the reference's aggr='mean')."""
+    """x_i' = aggr_{j->i} nn([x_i || x_j - x_i])   (PyG EdgeConv; the reference always passes aggr='mean')."""
 
     trans_inv = False
 
     def __init__(self, nn: torch.nn.Module, aggr: str = "mean"):
         super().__init__()
-        if aggr != "mean":
-            raise NotImplementedError(
-                f"EdgeConv(aggr={aggr!r}): only the reference's 'mean' aggregation (edge_conv_filter.py:11) is fused; "
-                "use stinet_b200.ops.aggregate for add/max over explicit messages")
+        if aggr not in ("mean", "add", "max"):
+            raise ValueError(f"EdgeConv(aggr={aggr!r}): expected 'mean' (the reference's choice, edge_conv_filter.py:11), "
+                             "'add' or 'max'")
         if not isinstance(nn, Seq):
             raise NotImplementedError("EdgeConv expects nn = torch.nn.Sequential (edge_conv_filter.py:34-55)")
-        # Sequential(Linear, ReLU, Linear) is evaluated in the hoisted form; anything else (the with_norm variant)
-        # literally, per edge
-        self.hoistable = (len(nn) == 3 and isinstance(nn[0], Lin) and isinstance(nn[2], Lin)
+        # Sequential(Linear, ReLU, Linear) under a mean is evaluated in the hoisted form; anything else (the with_norm
+        # variant; 'add' / 'max', through which the second Linear and its bias do not commute) literally, per edge
+        self.hoistable = (aggr == "mean" and len(nn) == 3 and isinstance(nn[0], Lin) and isinstance(nn[2], Lin)
                           and isinstance(nn[1], torch.nn.ReLU))
         self.nn = nn
         self.aggr = self._aggr = aggr
@@ -60,6 +59,10 @@ class EdgeConv(torch.nn.Module):
                 m = ops.linear(m, layer.weight, layer.bias, None, self.precision)
             else:
                 m = layer(m)
+        if self.aggr == "add":
+            return ops.pool_sum(m, by_target)
+        if self.aggr == "max":                       # first maximum wins, vertices without in-edges get 0 (torch_scatter)
+            return ops.pool_max(m, by_target)[0]
         return ops.pool_mean(m, by_target)
 
     def _fused_forward(self, x, csr):

@@ -865,6 +865,37 @@ def pool_mean(x, cl):
     return _carry_amax(x, PoolMeanFn.apply(x, cl))
 
 
+class PoolSumFn(Function):
+    """out[c] = sum of the rows of cluster c (in member order, deterministic): the adjoint pair of the row gather --
+    forward is stinet_unpool_bwd, backward stinet_unpool_fwd.  PyG's aggr='add' over per-edge messages."""
+
+    @staticmethod
+    def forward(ctx, x, cl: ClusterCSR):
+        x = _mat(x)
+        n, c = x.shape
+        assert n == cl.n_fine
+        out = torch.empty((cl.n_coarse, c), dtype=torch.float32, device=x.device)
+        _abi.call("stinet_unpool_bwd", x.data_ptr(), _ld(x), cl.rowptr.data_ptr(), cl.member.data_ptr(), cl.n_coarse, c,
+                  out.data_ptr(), c, _stream(), cost=(cl.n_fine * (4 * c + 4) + cl.n_coarse * 4 * c, 0, f"C{c}"))
+        ctx.cl = cl
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        cl = ctx.cl
+        g = _mat(g)
+        c = g.shape[1]
+        dx = torch.empty((cl.n_fine, c), dtype=torch.float32, device=g.device)
+        _abi.call("stinet_unpool_fwd", g.data_ptr(), _ld(g), cl.trace32.data_ptr(), cl.n_fine, c, dx.data_ptr(), c,
+                  _stream(), cost=(cl.n_fine * (4 + 8 * c), 0, f"C{c}"))
+        return dx, None
+
+
+def pool_sum(x, cl):
+    return PoolSumFn.apply(x, cl)
+
+
 def unpool(xc, cl):
     return _carry_amax(xc, UnpoolFn.apply(xc, cl))
 

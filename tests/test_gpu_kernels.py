@@ -162,6 +162,40 @@ def test_edge_conv_vs_literal_per_edge_mlp(kind, din, dout, trans_inv):
         assert float(out[(deg == 0).to(DEV)].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("kind", ["ico", "graph18_isolated", "multi_edges"])
+@pytest.mark.parametrize("aggr", ["add", "max"])
+@pytest.mark.parametrize("trans_inv", [False, True])
+def test_edge_conv_add_and_max_aggregation(kind, aggr, trans_inv):
+    """EdgeConv(aggr='add' | 'max') -- accepted by the reference's get_gcn_filter signature, never used by its configs --
+    runs the literal per-edge form (the second Linear does not commute with these reductions): values and gradients
+    against the oracle; vertices without in-edges output 0."""
+    from stinet_b200.models.modules import edge_conv_filter, edge_conv_translation_invariance
+    ei, n = _graph(kind)
+    din, dout = 8, 12
+    module = edge_conv_translation_invariance.EdgeConvTransInv if trans_inv else None
+    torch.manual_seed(7)
+    conv = edge_conv_filter.get_gcn_filter(din, dout, module=module, double_input=not trans_inv, aggregation=aggr)
+    assert not conv.hoistable
+    x = torch.randn(n, din)
+    go = torch.randn(n, dout)
+    xr = x.clone().requires_grad_(True)
+    ref = O.edge_conv(xr, ei, conv.nn, aggr, trans_inv)
+    ref.backward(go)
+    ref_grads = {k: p.grad.clone() for k, p in conv.named_parameters()}
+    conv.zero_grad()
+    conv = conv.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out = conv(xd, ei.to(DEV))
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= TOL
+    for k, p in conv.named_parameters():
+        assert rel_err(p.grad, ref_grads[k]) <= TOL, k
+    deg = torch.bincount(ei[1], minlength=n)
+    if (deg == 0).any():
+        assert float(out[(deg == 0).to(DEV)].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("c", [3, 8, 24, 64, 256, 1000])
 @pytest.mark.parametrize("pool", ["max", "mean"])
 def test_pool_unpool(c, pool):
