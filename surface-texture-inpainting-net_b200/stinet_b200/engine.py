@@ -104,10 +104,14 @@ class GraphedTrainStep:
         else:
             self.net.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.net(static), static)
-        if self.world > 1:
-            (loss * self.reducer.loss_scale).backward()  # mean over ranks = sum of the ranks' scaled gradients
-        else:
-            loss.backward()
+        from . import ops
+        # this step owns the backward call and nothing but the reducer and the optimizer reads the gradients: the weight
+        # gradients' stream is joined once, at the end (ops.deferred_wgrad_join)
+        with ops.deferred_wgrad_join():
+            if self.world > 1:
+                (loss * self.reducer.loss_scale).backward()  # mean over ranks = sum of the ranks' scaled gradients
+            else:
+                loss.backward()
         return loss
 
     def _finish(self):

@@ -51,12 +51,39 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 # the weight gradients (wgrad GEMM, its split reduction, the un-hoisting of dWcat) are leaves that nothing reads before
 # the optimizer.  They are launched on a second stream, so the tail of a dgrad kernel that no longer fills the 148 SMs
 # overlaps with the head of the wgrad next to it (and the other way round); in a captured step these are parallel branches
-# of the CUDA graph.  STINET_WGRAD_SIDE_STREAM = 0: one stream; 1: the node's backward joins before it returns;
-# 2 (default): joined once, at the end of the backward pass (autograd's final callback) and before a gradient bucket is
-# packed (parallel.GradAllReducer) -- buffers the second stream reads are then kept from reuse by record_stream.
-_WGRAD_SIDE = int(os.environ.get("STINET_WGRAD_SIDE_STREAM", "2"))
+# of the CUDA graph.  Two ways to rejoin:
+#   * per node (default, safe under any caller): the node's backward waits for the second stream before it returns, so
+#     whatever autograd or a hook does with the gradient next is ordered after it;
+#   * deferred (inside `deferred_wgrad_join()`, which engine.GraphedTrainStep enters around its backward): one join at
+#     the end of the backward pass (autograd's final callback), and one before GradAllReducer packs a bucket.  Nothing on
+#     the main stream may touch such a gradient earlier, so the node does not hand it to autograd at all (whether
+#     AccumulateGrad keeps a gradient by reference or copies it is its own business -- under compute-sanitizer it
+#     copies): it deposits it in `.grad` itself and calls the reducer's hook, which is what AccumulateGrad would have done
+#     for a leaf parameter without a gradient.  Weights that do not qualify (`_straight_to_grad`) join per node.
+# STINET_WGRAD_SIDE_STREAM = 0: one stream; 1 (default): as above; 2: deferred everywhere.
+_WGRAD_SIDE = int(os.environ.get("STINET_WGRAD_SIDE_STREAM", "1"))
 _WGRAD_STREAMS = {}
 _wgrad_join_due = set()
+_defer_depth = 0
+
+
+class deferred_wgrad_join:
+    """with deferred_wgrad_join(): loss.backward()   -- see above.  The caller owns the backward call and promises that
+    nothing but the optimizer (or GradAllReducer) reads the parameters' gradients before backward() has returned."""
+
+    def __enter__(self):
+        global _defer_depth
+        _defer_depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _defer_depth
+        _defer_depth -= 1
+        return False
+
+
+def _deferring() -> bool:
+    return _WGRAD_SIDE == 2 or (_WGRAD_SIDE == 1 and _defer_depth > 0)
 
 
 def _wgrad_stream(dev: torch.device):
@@ -78,7 +105,7 @@ class _on_wgrad_stream:
             return self
         main, side = torch.cuda.current_stream(self.dev), _wgrad_stream(self.dev)
         side.wait_stream(main)
-        if _WGRAD_SIDE == 2:
+        if _deferring():                             # the reader may still be running when the caller drops its buffers
             for r in self.reads:
                 for t in ((r.hi, r.lo, r.exp) if isinstance(r, Planes) else (r,)):
                     if t is not None:
@@ -103,11 +130,10 @@ def join_wgrad_stream(dev=None) -> None:
 
 
 def _straight_to_grad(*weights) -> bool:
-    """True when the gradients of these weights go from the backward straight into `.grad` by reference (leaf parameter,
-    no gradient yet, no tensor hooks, post-accumulate hooks only from GradAllReducer, which joins before it packs):
-    nothing on the current stream reads them before the end of the backward pass, so their join can wait until then.
-    A weight that is itself a function of a parameter (a padded or hoisted copy) has an autograd node downstream that
-    reads the gradient at once -- its backward joins before it returns."""
+    """True when these weights are leaf parameters without a gradient yet, without tensor hooks, and with post-accumulate
+    hooks only from GradAllReducer (which joins before it packs): depositing the gradient in `.grad` is then all that
+    autograd would do with it.  A weight that is itself a function of a parameter (a padded or hoisted copy) has an
+    autograd node downstream that reads the gradient at once."""
     for w in weights:
         if w is None:
             continue
@@ -118,20 +144,31 @@ def _straight_to_grad(*weights) -> bool:
     return True
 
 
-def _wgrad_done(dev, outs, defer_ok: bool = True) -> None:
-    """End of a backward that used _on_wgrad_stream: `outs` were produced there and are consumed on the current stream."""
-    if not _WGRAD_SIDE:
-        return
+def _wgrad_done(dev, pairs):
+    """End of a backward that used _on_wgrad_stream.  pairs: [(weight, gradient produced on the second stream or None)].
+    Returns the gradients to hand to autograd, in order: the tensors themselves after a join, or None for those that were
+    deposited in `.grad` here (deferred join)."""
+    grads = [g for _, g in pairs]
+    if not _WGRAD_SIDE or all(g is None for g in grads):
+        return grads
     main = torch.cuda.current_stream(dev)
-    for t in outs:
-        if t is not None:
-            t.record_stream(main)
+    for g in grads:
+        if g is not None:
+            g.record_stream(main)
     k = dev.index if dev.index is not None else torch.cuda.current_device()
     _wgrad_join_due.add(k)
-    if _WGRAD_SIDE == 1 or not defer_ok:
+    if not (_deferring() and _straight_to_grad(*[w for w, g in pairs if g is not None])):
         join_wgrad_stream(dev)
-    else:                                            # idempotent: the first one to run joins, the others find nothing due
-        torch.autograd.Variable._execution_engine.queue_callback(lambda: join_wgrad_stream(dev))
+        return grads
+    # idempotent: the first callback to run joins, the others find nothing due
+    torch.autograd.Variable._execution_engine.queue_callback(lambda: join_wgrad_stream(dev))
+    for w, g in pairs:
+        if g is None:
+            continue
+        w.grad = g
+        for hook in list((getattr(w, "_post_accumulate_grad_hooks", None) or {}).values()):
+            hook(w)
+    return [None] * len(grads)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -436,8 +473,7 @@ class LinearPlanesFn(Function):
                 dw = _pl_wgrad(dyp, xp, passes)
         if ctx.needs_input_grad[0]:
             dx, _ = _pl_dgrad(dyp, wp, passes)
-        if dw is not None:
-            _wgrad_done(dev, (dw,), _straight_to_grad(*ctx.weights))
+        (dw,) = _wgrad_done(dev, [(ctx.weights[0], dw)])
         return dx, dw, db, None, None
 
 
@@ -535,8 +571,7 @@ class EdgeConvFn(Function):
                 _abi.call("stinet_edgeconv_hoist_bwd", dwcat.data_ptr(), None, h, din, int(trans_inv), dw0.data_ptr(), kin,
                           None, _stream(), cost=(4 * h * (kin + 2 * din), 0, ""))
         dx = _pl_dgrad(dpqp, wcp, passes)[0] if ctx.needs_input_grad[0] else None
-        if dw0 is not None or dw2 is not None:
-            _wgrad_done(dev, (dw0, dw2), _straight_to_grad(*ctx.weights))
+        dw0, dw2 = _wgrad_done(dev, [(ctx.weights[0], dw0), (ctx.weights[1], dw2)])
         return dx, dw0, db0, dw2, db2, None, None, None
 
 

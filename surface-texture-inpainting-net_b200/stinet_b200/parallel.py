@@ -62,6 +62,7 @@ class GradAllReducer:
         self._pending: List[int] = []
         self._issued: List[bool] = []
         self._handles = []
+        self._counted = set()
         if self.world == 1:
             return
         # reverse order: the last layers' gradients are produced first
@@ -98,6 +99,7 @@ class GradAllReducer:
             self._pending = list(self._sizes)
             self._issued = [False] * len(self._groups)
             self._handles = []
+            self._counted = set()
 
     def _issue(self, b: int):
         """Pack bucket b (one multi-tensor copy; a parameter without a gradient contributes zeros), re-point the .grad of
@@ -119,6 +121,11 @@ class GradAllReducer:
     def _on_grad(self, p):
         if not (self.enabled and self.overlap):
             return
+        # once per parameter and step: a node that deposits a weight gradient itself (ops._wgrad_done) calls this hook, and
+        # autograd may call it again for the same parameter although it was handed no gradient
+        if id(p) in self._counted:
+            return
+        self._counted.add(id(p))
         b = self._bucket_of[p]
         self._pending[b] -= 1
         if self._pending[b] == 0 and not self._issued[b]:

@@ -85,3 +85,48 @@ def test_side_streams_inside_a_captured_step(monkeypatch, wgrad_side):
     assert l0 == l1, (l0, l1)
     for a, b in zip(p0, p1):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("aware", [True, False])
+def test_gradient_hooks_see_finished_gradients(monkeypatch, aware):
+    """Post-accumulate hooks (what GradAllReducer hangs on every parameter) under the deferred join: a hook flagged as
+    aware of the second stream joins it itself (ops.join_wgrad_stream) and then reads the deposited gradient; an unflagged
+    (foreign) hook makes the producing node join before it returns.  Either way the gradient a hook reads is the
+    one-stream gradient, bit for bit, and every parameter's hook runs at least once."""
+    from stinet_b200 import ops
+    monkeypatch.setenv("STINET_STRUCT_SIDE_STREAM", "0")
+    net = _net()
+    names = {p: n for n, p in net.named_parameters()}
+    seen = {}
+
+    def hook(p):
+        if aware:
+            ops.join_wgrad_stream()
+        seen.setdefault(names[p], p.grad.detach().clone())
+
+    def step(mode, defer):
+        monkeypatch.setattr(ops, "_WGRAD_SIDE", mode)
+        seen.clear()
+        b = _make(49).to(DEV)
+        for p in net.parameters():
+            p.grad = None
+        loss = _loss(net(b), b)
+        if defer:
+            with ops.deferred_wgrad_join():
+                loss.backward()
+        else:
+            loss.backward()
+        torch.cuda.synchronize()
+        return dict(seen), {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+
+    _, ref = step(0, False)
+    for p in net.parameters():
+        p.register_post_accumulate_grad_hook(hook)
+        if aware:
+            p._stinet_wgrad_aware = True
+    for mode, defer in [(1, False), (1, True), (2, False)]:
+        at_hook, final = step(mode, defer)
+        assert set(at_hook) == set(ref)
+        for n in ref:
+            assert torch.equal(at_hook[n], ref[n]), (mode, defer, n)
+            assert torch.equal(final[n], ref[n]), (mode, defer, n)
