@@ -1,7 +1,6 @@
 #!/bin/bash
-OUT=gpurun_out
-python __graft_entry__.py 2>&1 | tail -1
-( timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > $OUT/pytest_r2_zz.log 2>&1; echo "pytest exit $?"; grep -E "passed|failed" $OUT/pytest_r2_zz.log | tail -1; grep -E "^(FAILED|ERROR)" $OUT/pytest_r2_zz.log | head
-timeout 400 python bench.py --steps 20 --warmup 5 --kernels-out $OUT/kernels_r2_zz.json > $OUT/bench_r2_zz.json 2> $OUT/bench_r2_zz.err; echo "bench exit $?"
-python -c "
-import json; b=json.load(open('$OUT/bench_r2_zz.json')); print('bench', b['ms_per_step'], b['value'], b['e2e']['value'], b['roofline']['achieved'], b['roofline']['frac'], b['gpu_launches'])"
+OUT=gpurun_out; mkdir -p $OUT
+N=${1:-4}
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-cached > $OUT/bench_r2_zz_n$N.json 2> $OUT/bench_r2_zz_n$N.err
+echo "n$N exit $?"; python -c "
+import json; b=json.load(open('$OUT/bench_r2_zz_n$N.json')); print(b['n_gpus'], b['ms_per_step'], b['value'], b['e2e']['value'], b['clocks'])" || tail -20 $OUT/bench_r2_zz_n$N.err
