@@ -130,3 +130,27 @@ def test_gradient_hooks_see_finished_gradients(monkeypatch, aware):
         for n in ref:
             assert torch.equal(at_hook[n], ref[n]), (mode, defer, n)
             assert torch.equal(final[n], ref[n]), (mode, defer, n)
+
+
+def test_gradient_accumulation_under_deferred_join(monkeypatch):
+    """Two backward passes without zeroing in between: the second one finds `.grad` occupied, so its weight gradients go
+    through autograd's own accumulation (per-node join) instead of being deposited -- the sum must be exactly what the
+    one-stream schedule accumulates."""
+    from stinet_b200 import ops
+    monkeypatch.setenv("STINET_STRUCT_SIDE_STREAM", "0")
+
+    def run(mode):
+        monkeypatch.setattr(ops, "_WGRAD_SIDE", mode)
+        net = _net()
+        for seed in (49, 50):
+            b = _make(seed).to(DEV)
+            loss = _loss(net(b), b)
+            with ops.deferred_wgrad_join():
+                loss.backward()
+        torch.cuda.synchronize()
+        return [p.grad.detach().clone() for p in net.parameters()]
+
+    ref = run(0)
+    for mode in (1, 2):
+        for a, b in zip(ref, run(mode)):
+            assert torch.equal(a, b)
